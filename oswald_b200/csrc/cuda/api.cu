@@ -1,0 +1,551 @@
+// api.cu - the C ABI (include/oswald_cuda.h): context, database upload, search orchestration.
+//
+// One DevState per GPU: its shard of the chunk streams resident in HBM, one stream, events.
+// osw_search enqueues, per GPU and without host synchronisation in between:
+//   score clear -> first-stage launches (one per query pair and pass) -> flagged-pair scan,
+// then (after reading each GPU's flagged count) 32-bit re-score -> top-r radix select,
+// and only then waits for all GPUs, orders the r keys per query on the host and merges the
+// GPUs' lists (the reference's sort_scores order, utils.c:3-86).
+#include "osw_internal.h"
+#include <algorithm>
+#include <chrono>
+#include <new>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+static thread_local char g_err[512];
+static int cuda_fail(cudaError_t e, const char *what, int line) {
+    snprintf(g_err, sizeof g_err, "%s failed at api.cu:%d: %s", what, line, cudaGetErrorString(e));
+    return OSW_E_CUDA;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call, __LINE__); } while (0)
+
+namespace {
+
+constexpr uint32_t MAX_LAUNCH_SLOTS = 4096;
+constexpr uint32_t FLAG_CAPACITY_MIN = 1u << 16;
+
+struct DevState {
+    int dev = -1, n_sms = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[6] = {};
+    // database shard
+    osw_shard shard = {};
+    uint8_t *h_stream = nullptr;               // pinned copy of shard.stream (source of re-uploads)
+    uint8_t *d_stream = nullptr; osw_chunk *d_chunks = nullptr; uint32_t *d_canon = nullptr;
+    uint64_t *d_seq_off = nullptr; uint32_t *d_seq_len = nullptr;
+    // per-search buffers (grown on demand)
+    int32_t *d_scores = nullptr; size_t scores_cap = 0;
+    uint8_t *d_queries = nullptr; size_t queries_cap = 0;
+    uint32_t *d_qoff = nullptr; size_t qoff_cap = 0;
+    int8_t *d_matrix = nullptr;
+    int2 *d_scratch = nullptr; size_t scratch_cap = 0;
+    uint2 *d_bound[2] = {nullptr, nullptr};
+    uint2 *d_pairs = nullptr; uint32_t pairs_cap = 0;
+    uint32_t *d_counters = nullptr;            // [0] flagged count, [1..] chunk counters per launch
+    unsigned long long *d_task_counter = nullptr;   // [0] i32 queue, [1] n_tasks mirror
+    unsigned long long *d_cycles = nullptr;    // [MAX_LAUNCH_SLOTS]
+    TopRWork topr = {}; int topr_nq = 0; uint32_t topr_r = 0;
+    unsigned long long *h_keys = nullptr; size_t h_keys_cap = 0;      // pinned
+    int32_t *h_scores = nullptr; size_t h_scores_cap = 0;             // pinned
+    unsigned long long *h_cycles = nullptr;                            // pinned [MAX_LAUNCH_SLOTS]
+    uint32_t *h_counts = nullptr;                                       // pinned [4]
+};
+
+template <typename T>
+int grow(T **ptr, size_t *cap, size_t need) {
+    if (need <= *cap) return OSW_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc((void **)ptr, need * sizeof(T));
+    if (e != cudaSuccess) { cuda_fail(e, "cudaMalloc", __LINE__); return OSW_E_NOMEM; }
+    *cap = need;
+    return OSW_OK;
+}
+template <typename T>
+int grow_pinned(T **ptr, size_t *cap, size_t need) {
+    if (need <= *cap) return OSW_OK;
+    if (*ptr) cudaFreeHost(*ptr);
+    *ptr = nullptr; *cap = 0;
+    cudaError_t e = cudaMallocHost((void **)ptr, need * sizeof(T));
+    if (e != cudaSuccess) { cuda_fail(e, "cudaMallocHost", __LINE__); return OSW_E_NOMEM; }
+    *cap = need;
+    return OSW_OK;
+}
+
+void free_db(DevState &d) {
+    cudaSetDevice(d.dev);
+    cudaFree(d.d_stream); cudaFree(d.d_chunks); cudaFree(d.d_canon); cudaFree(d.d_seq_off); cudaFree(d.d_seq_len);
+    cudaFree(d.d_bound[0]); cudaFree(d.d_bound[1]);
+    d.d_stream = nullptr; d.d_chunks = nullptr; d.d_canon = nullptr; d.d_seq_off = nullptr; d.d_seq_len = nullptr;
+    d.d_bound[0] = d.d_bound[1] = nullptr;
+    if (d.h_stream) cudaFreeHost(d.h_stream);
+    d.h_stream = nullptr;
+    osw_shard_free(&d.shard);
+}
+
+int upload_db(DevState &d) {
+    const osw_shard &s = d.shard;
+    CK(cudaSetDevice(d.dev));
+    CK(cudaMemcpyAsync(d.d_stream, d.h_stream, s.stream_bytes, cudaMemcpyHostToDevice, d.st));
+    CK(cudaMemcpyAsync(d.d_chunks, s.chunks, s.n_chunks * sizeof(osw_chunk), cudaMemcpyHostToDevice, d.st));
+    CK(cudaMemcpyAsync(d.d_canon, s.canon, s.n_seqs * sizeof(uint32_t), cudaMemcpyHostToDevice, d.st));
+    CK(cudaMemcpyAsync(d.d_seq_off, s.seq_off, s.n_seqs * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st));
+    CK(cudaMemcpyAsync(d.d_seq_len, s.seq_len, s.n_seqs * sizeof(uint32_t), cudaMemcpyHostToDevice, d.st));
+    return OSW_OK;
+}
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct osw_ctx {
+    int n_dev = 0;
+    DevState *devs = nullptr;
+    int kernel_mask = OSW_K_DEFAULT;
+    bool db_loaded = false;
+    uint64_t n_seqs_canon = 0;        // size of the whole canonical database
+    uint64_t n_seqs_local = 0, residues_local = 0, chunks_local = 0;
+};
+
+extern "C" const char *osw_strerror(int code) {
+    switch (code) {
+        case OSW_OK: return "ok";
+        case OSW_E_ARG: return "invalid argument";
+        case OSW_E_NODEV: return "no usable CUDA device";
+        case OSW_E_CUDA: return "CUDA runtime error";
+        case OSW_E_NOMEM: return "out of memory";
+        case OSW_E_STATE: return "call order error (database not loaded?)";
+        case OSW_E_ARCH: return "device is not sm_100 (B200)";
+    }
+    return "unknown error";
+}
+extern "C" const char *osw_last_error(void) { return g_err; }
+
+extern "C" int osw_device_count(int *count) {
+    if (!count) return OSW_E_ARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; cuda_fail(e, "cudaGetDeviceCount", __LINE__); return OSW_E_NODEV; }
+    *count = n;
+    return OSW_OK;
+}
+
+extern "C" int osw_device_info(int device, char *text, size_t n) {
+    if (!text || !n) return OSW_E_ARG;
+    cudaDeviceProp pr;
+    cudaError_t e = cudaGetDeviceProperties(&pr, device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties", __LINE__);
+    int clock_khz = 0, mem_khz = 0;
+    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, device);
+    cudaDeviceGetAttribute(&mem_khz, cudaDevAttrMemoryClockRate, device);
+    snprintf(text, n,
+             "Device %d: %s\n  compute capability %d.%d, %d SMs, %.0f MHz\n  global memory %.1f GiB, memory clock %.0f MHz, L2 %.0f MiB\n"
+             "  shared memory per block (opt-in) %zu KiB, registers per SM %d\n",
+             device, pr.name, pr.major, pr.minor, pr.multiProcessorCount, clock_khz / 1000.0,
+             pr.totalGlobalMem / 1073741824.0, mem_khz / 1000.0, pr.l2CacheSize / 1048576.0,
+             pr.sharedMemPerBlockOptin / 1024, pr.regsPerMultiprocessor);
+    return OSW_OK;
+}
+
+extern "C" int osw_init(int n_devices, const int *devices, osw_ctx **out) {
+    if (!out || n_devices < 1) return OSW_E_ARG;
+    *out = nullptr;
+    int avail = 0;
+    int rc = osw_device_count(&avail);
+    if (rc != OSW_OK || avail < 1) return OSW_E_NODEV;
+    osw_ctx *c = new (std::nothrow) osw_ctx;
+    if (!c) return OSW_E_NOMEM;
+    c->devs = new (std::nothrow) DevState[n_devices];
+    if (!c->devs) { delete c; return OSW_E_NOMEM; }
+    c->n_dev = n_devices;
+    for (int i = 0; i < n_devices; ++i) {
+        DevState &d = c->devs[i];
+        d.dev = devices ? devices[i] : i;
+        if (d.dev < 0 || d.dev >= avail) { osw_free(c); return OSW_E_NODEV; }
+        cudaDeviceProp pr;
+        cudaError_t e = cudaGetDeviceProperties(&pr, d.dev);
+        if (e != cudaSuccess) { osw_free(c); return cuda_fail(e, "cudaGetDeviceProperties", __LINE__); }
+        if (pr.major != 10) {
+            snprintf(g_err, sizeof g_err, "device %d (%s) is sm_%d%d; this library is built for sm_100a only",
+                     d.dev, pr.name, pr.major, pr.minor);
+            osw_free(c);
+            return OSW_E_ARCH;
+        }
+        d.n_sms = pr.multiProcessorCount;
+        if ((e = cudaSetDevice(d.dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking)) != cudaSuccess) {
+            osw_free(c); return cuda_fail(e, "stream setup", __LINE__);
+        }
+        for (auto &ev : d.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) { osw_free(c); return cuda_fail(e, "cudaEventCreate", __LINE__); }
+        if ((e = cudaMalloc(&d.d_matrix, 24 * 32)) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_counters, (1 + MAX_LAUNCH_SLOTS) * sizeof(uint32_t))) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_task_counter, 2 * sizeof(unsigned long long))) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_cycles, MAX_LAUNCH_SLOTS * sizeof(unsigned long long))) != cudaSuccess ||
+            (e = cudaMallocHost(&d.h_cycles, MAX_LAUNCH_SLOTS * sizeof(unsigned long long))) != cudaSuccess ||
+            (e = cudaMallocHost(&d.h_counts, 4 * sizeof(uint32_t))) != cudaSuccess) {
+            osw_free(c); return cuda_fail(e, "cudaMalloc", __LINE__);
+        }
+    }
+    *out = c;
+    return OSW_OK;
+}
+
+extern "C" void osw_free(osw_ctx *c) {
+    if (!c) return;
+    for (int i = 0; i < c->n_dev; ++i) {
+        DevState &d = c->devs[i];
+        if (d.dev < 0) continue;
+        cudaSetDevice(d.dev);
+        if (d.st) cudaStreamSynchronize(d.st);
+        free_db(d);
+        cudaFree(d.d_scores); cudaFree(d.d_queries); cudaFree(d.d_qoff); cudaFree(d.d_matrix); cudaFree(d.d_scratch);
+        cudaFree(d.d_pairs); cudaFree(d.d_counters); cudaFree(d.d_task_counter); cudaFree(d.d_cycles);
+        cudaFree(d.topr.hist); cudaFree(d.topr.prefix); cudaFree(d.topr.remaining); cudaFree(d.topr.out_count); cudaFree(d.topr.out_keys);
+        if (d.h_keys) cudaFreeHost(d.h_keys);
+        if (d.h_scores) cudaFreeHost(d.h_scores);
+        if (d.h_cycles) cudaFreeHost(d.h_cycles);
+        if (d.h_counts) cudaFreeHost(d.h_counts);
+        for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
+        if (d.st) cudaStreamDestroy(d.st);
+    }
+    delete[] c->devs;
+    delete c;
+}
+
+extern "C" int osw_set_kernels(osw_ctx *c, int mask) {
+    if (!c || !(mask & (OSW_K_U16 | OSW_K_I32)) || !(mask & OSW_K_I32)) return OSW_E_ARG;   // the 32-bit stage is never optional
+    c->kernel_mask = mask;
+    return OSW_OK;
+}
+
+extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
+                           int shard_rank, int shard_count, uint64_t max_chunk_residues) {
+    if (!c || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return OSW_E_ARG;
+    if (n_seqs && (!residues || !offsets)) return OSW_E_ARG;
+    if (n_seqs > 0xffffffffull) return OSW_E_ARG;
+    uint32_t chunk_cols = OSW_CHUNK_COLS_DEFAULT;
+    if (max_chunk_residues && max_chunk_residues < chunk_cols) chunk_cols = (uint32_t)max_chunk_residues;
+    const uint32_t n_shards = (uint32_t)shard_count * (uint32_t)c->n_dev;
+    c->db_loaded = false;
+    c->n_seqs_canon = n_seqs; c->n_seqs_local = 0; c->residues_local = 0; c->chunks_local = 0;
+    for (int i = 0; i < c->n_dev; ++i) {
+        DevState &d = c->devs[i];
+        free_db(d);
+        if (osw_shard_build(residues, offsets, n_seqs, (uint32_t)shard_rank * c->n_dev + i, n_shards, chunk_cols, &d.shard) != 0)
+            return OSW_E_NOMEM;
+        const osw_shard &s = d.shard;
+        CK(cudaSetDevice(d.dev));
+        CK(cudaMalloc(&d.d_stream, s.stream_bytes ? s.stream_bytes : 1));
+        CK(cudaMalloc(&d.d_chunks, (s.n_chunks ? s.n_chunks : 1) * sizeof(osw_chunk)));
+        CK(cudaMalloc(&d.d_canon, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint32_t)));
+        CK(cudaMalloc(&d.d_seq_off, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint64_t)));
+        CK(cudaMalloc(&d.d_seq_len, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint32_t)));
+        CK(cudaMallocHost(&d.h_stream, s.stream_bytes ? s.stream_bytes : 1));
+        memcpy(d.h_stream, s.stream, s.stream_bytes);
+        free(d.shard.stream); d.shard.stream = nullptr;      // the pinned copy is the one kept
+        int rc = upload_db(d);
+        if (rc != OSW_OK) return rc;
+        c->n_seqs_local += s.n_seqs; c->residues_local += s.n_residues; c->chunks_local += s.n_chunks;
+    }
+    for (int i = 0; i < c->n_dev; ++i) {
+        DevState &d = c->devs[i];
+        CK(cudaSetDevice(d.dev));
+        CK(cudaStreamSynchronize(d.st));
+    }
+    c->db_loaded = true;
+    return OSW_OK;
+}
+
+extern "C" int osw_db_upload(osw_ctx *c, uint64_t *bytes) {
+    if (!c || !c->db_loaded) return OSW_E_STATE;
+    uint64_t total = 0;
+    for (int i = 0; i < c->n_dev; ++i) {
+        int rc = upload_db(c->devs[i]);
+        if (rc != OSW_OK) return rc;
+        const osw_shard &s = c->devs[i].shard;
+        total += s.stream_bytes + s.n_chunks * sizeof(osw_chunk) + s.n_seqs * (sizeof(uint32_t) * 2 + sizeof(uint64_t));
+    }
+    for (int i = 0; i < c->n_dev; ++i) {
+        CK(cudaSetDevice(c->devs[i].dev));
+        CK(cudaStreamSynchronize(c->devs[i].st));
+    }
+    if (bytes) *bytes = total;
+    return OSW_OK;
+}
+
+extern "C" int osw_db_stats(const osw_ctx *c, uint64_t *n_seqs_local, uint64_t *residues_local, uint64_t *n_chunks_local) {
+    if (!c || !c->db_loaded) return OSW_E_STATE;
+    if (n_seqs_local) *n_seqs_local = c->n_seqs_local;
+    if (residues_local) *residues_local = c->residues_local;
+    if (n_chunks_local) *n_chunks_local = c->chunks_local;
+    return OSW_OK;
+}
+
+// Orders two hits like the reference's merge sort leaves them (utils.c:3-69).
+static inline bool hit_before(const osw_hit &a, const osw_hit &b) {
+    return a.score != b.score ? a.score > b.score : a.index > b.index;
+}
+
+extern "C" size_t osw_merge_hits(const osw_hit *const *lists, const uint32_t *counts, int n_lists,
+                                 uint32_t top_r, osw_hit *out) {
+    if (!lists || !counts || !out || n_lists < 1) return 0;
+    std::vector<uint32_t> cur((size_t)n_lists, 0u);
+    size_t n = 0;
+    while (n < top_r) {
+        int pick = -1;
+        for (int s = 0; s < n_lists; ++s) {
+            if (cur[s] >= counts[s]) continue;
+            if (pick < 0 || hit_before(lists[s][cur[s]], lists[pick][cur[pick]])) pick = s;
+        }
+        if (pick < 0) break;
+        out[n++] = lists[pick][cur[pick]++];
+    }
+    return n;
+}
+
+namespace {
+
+struct QueryPair { int a, b; uint32_t len_a, len_b; U16Config cfg; };
+
+// Pairs queries of similar length (longest first); with an odd count the shortest stays single.
+void plan_pairs(const uint32_t *q_off, int nq, std::vector<QueryPair> &pairs) {
+    std::vector<int> order(nq);
+    for (int i = 0; i < nq; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        return q_off[x + 1] - q_off[x] > q_off[y + 1] - q_off[y];
+    });
+    for (int i = 0; i < nq; i += 2) {
+        QueryPair p;
+        p.a = order[i]; p.len_a = q_off[p.a + 1] - q_off[p.a];
+        if (i + 1 < nq) { p.b = order[i + 1]; p.len_b = q_off[p.b + 1] - q_off[p.b]; }
+        else { p.b = -1; p.len_b = 0; }
+        osw_u16_plan(std::max(p.len_a, p.len_b), &p.cfg);
+        pairs.push_back(p);
+    }
+}
+
+int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32_t *q_off, int nq,
+                   const int8_t *matrix, int go, int ge, uint32_t top_r, bool want_all,
+                   const std::vector<QueryPair> &pairs, uint32_t *n_launch_slots, uint64_t *launches,
+                   uint64_t *padded_cells) {
+    const osw_shard &s = d.shard;
+    const uint64_t N = s.n_seqs;
+    const size_t q_bytes = q_off[nq];
+    CK(cudaSetDevice(d.dev));
+    int rc;
+    if ((rc = grow(&d.d_scores, &d.scores_cap, (size_t)nq * (N ? N : 1))) != OSW_OK) return rc;
+    if ((rc = grow(&d.d_queries, &d.queries_cap, q_bytes ? q_bytes : 1)) != OSW_OK) return rc;
+    if ((rc = grow(&d.d_qoff, &d.qoff_cap, (size_t)nq + 1)) != OSW_OK) return rc;
+    const uint32_t r = (uint32_t)std::min<uint64_t>(top_r, N);
+    if (nq > d.topr_nq || r > d.topr_r) {
+        cudaFree(d.topr.hist); cudaFree(d.topr.prefix); cudaFree(d.topr.remaining); cudaFree(d.topr.out_count); cudaFree(d.topr.out_keys);
+        d.topr = TopRWork(); d.topr_nq = 0; d.topr_r = 0;
+        const int qn = std::max(nq, d.topr_nq); const uint32_t rn = std::max(r, std::max(d.topr_r, 1u));
+        CK(cudaMalloc(&d.topr.hist, (size_t)qn * 256 * sizeof(uint32_t)));
+        CK(cudaMalloc(&d.topr.prefix, (size_t)qn * sizeof(unsigned long long)));
+        CK(cudaMalloc(&d.topr.remaining, (size_t)qn * sizeof(uint32_t)));
+        CK(cudaMalloc(&d.topr.out_count, (size_t)qn * sizeof(uint32_t)));
+        CK(cudaMalloc(&d.topr.out_keys, (size_t)qn * rn * sizeof(unsigned long long)));
+        d.topr_nq = qn; d.topr_r = rn;
+    }
+    if ((rc = grow_pinned(&d.h_keys, &d.h_keys_cap, (size_t)nq * std::max(r, 1u))) != OSW_OK) return rc;
+    if (want_all && (rc = grow_pinned(&d.h_scores, &d.h_scores_cap, (size_t)nq * (N ? N : 1))) != OSW_OK) return rc;
+
+    const bool use_u16 = (c->kernel_mask & OSW_K_U16) != 0;
+    // 32-bit kernel geometry and scratch
+    const int i32_blocks = d.n_sms * 4;
+    const size_t warps = (size_t)i32_blocks * (osw_i32_block_threads() / 32);
+    if ((rc = grow(&d.d_scratch, &d.scratch_cap, warps * (s.max_len ? s.max_len : 1))) != OSW_OK) return rc;
+    uint32_t flag_cap = 0;
+    if (use_u16) {
+        uint64_t want = std::max<uint64_t>(FLAG_CAPACITY_MIN, (uint64_t)nq * N / 64);
+        flag_cap = (uint32_t)std::min<uint64_t>(want, 1u << 26);
+        size_t cap = d.pairs_cap;
+        if ((rc = grow(&d.d_pairs, &cap, flag_cap)) != OSW_OK) return rc;
+        d.pairs_cap = (uint32_t)cap;
+        flag_cap = d.pairs_cap;
+        bool need_bound = false;
+        for (const QueryPair &p : pairs) need_bound |= p.cfg.passes > 1;
+        if (need_bound && !d.d_bound[0]) {
+            for (int k = 0; k < 2; ++k) {
+                CK(cudaMalloc(&d.d_bound[k], (s.stream_bytes ? s.stream_bytes : 1) * sizeof(uint2)));
+                CK(cudaMemsetAsync(d.d_bound[k], 0, (s.stream_bytes ? s.stream_bytes : 1) * sizeof(uint2), d.st));
+            }
+        }
+    }
+
+    // ---- uploads ----
+    CK(cudaMemcpyAsync(d.d_queries, queries, q_bytes, cudaMemcpyHostToDevice, d.st));
+    CK(cudaMemcpyAsync(d.d_qoff, q_off, ((size_t)nq + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, d.st));
+    CK(cudaMemcpyAsync(d.d_matrix, matrix, 24 * 32, cudaMemcpyHostToDevice, d.st));
+    CK(cudaEventRecord(d.ev[0], d.st));
+    CK(cudaMemsetAsync(d.d_scores, 0, (size_t)nq * N * sizeof(int32_t), d.st));
+    CK(cudaMemsetAsync(d.d_counters, 0, (1 + MAX_LAUNCH_SLOTS) * sizeof(uint32_t), d.st));
+    CK(cudaMemsetAsync(d.d_task_counter, 0, 2 * sizeof(unsigned long long), d.st));
+    CK(cudaMemsetAsync(d.d_cycles, 0, MAX_LAUNCH_SLOTS * sizeof(unsigned long long), d.st));
+
+    uint32_t slot = 0;
+    if (use_u16 && N) {
+        for (const QueryPair &qp : pairs) {
+            const uint32_t rows_per_pass = (uint32_t)(qp.cfg.G * qp.cfg.R);
+            for (int pass = 0; pass < qp.cfg.passes; ++pass) {
+                if (slot >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
+                U16Params up;
+                up.stream = d.d_stream; up.chunks = d.d_chunks; up.n_chunks = s.n_chunks;
+                up.query_a = d.d_queries + q_off[qp.a]; up.len_a = qp.len_a;
+                up.query_b = qp.b >= 0 ? d.d_queries + q_off[qp.b] : d.d_queries; up.len_b = qp.len_b;
+                up.matrix = d.d_matrix;
+                up.scores_a = d.d_scores + (size_t)qp.a * N;
+                up.scores_b = qp.b >= 0 ? d.d_scores + (size_t)qp.b * N : nullptr;
+                up.bound_in = pass > 0 ? d.d_bound[(pass - 1) & 1] : nullptr;
+                up.bound_out = pass + 1 < qp.cfg.passes ? d.d_bound[pass & 1] : nullptr;
+                up.row0 = (uint32_t)pass * rows_per_pass;
+                up.gap_open_extend = go + ge; up.gap_extend = ge;
+                up.chunk_counter = d.d_counters + 1 + slot;
+                up.cycle_acc = d.d_cycles + slot;
+                if ((rc = osw_launch_u16(up, qp.cfg, d.n_sms, d.st)) != OSW_OK) {
+                    cuda_fail(cudaGetLastError(), "sw_u16 launch", __LINE__);
+                    return rc;
+                }
+                ++slot; ++*launches;
+                *padded_cells += (uint64_t)rows_per_pass * 2 * s.n_residues;
+            }
+        }
+        CK(cudaEventRecord(d.ev[1], d.st));
+        *launches += osw_collect_flagged(d.d_scores, N, nq, d.d_pairs, d.d_counters, flag_cap, d.st);
+        CK(cudaMemcpyAsync(d.h_counts, d.d_counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, d.st));
+    } else {
+        CK(cudaEventRecord(d.ev[1], d.st));
+    }
+    *n_launch_slots = slot;
+    return OSW_OK;
+}
+
+}  // namespace
+
+extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_off, int nq,
+                          const int8_t *matrix, int go, int ge, int top_r,
+                          osw_hit *hits, uint32_t *n_hits, int32_t *all_scores, osw_timing *timing) {
+    if (!c || !queries || !q_off || nq < 1 || !matrix || go < 0 || ge < 0 || go > 255 || ge > 127 || top_r < 0)
+        return OSW_E_ARG;
+    if (top_r > 0 && !hits) return OSW_E_ARG;
+    if (!c->db_loaded) return OSW_E_STATE;
+    for (int q = 0; q < nq; ++q)
+        if (q_off[q + 1] < q_off[q] || q_off[q + 1] - q_off[q] > OSW_MAX_QUERY_LEN) return OSW_E_ARG;
+    const double t_wall0 = now_ms();
+    std::vector<QueryPair> pairs;
+    plan_pairs(q_off, nq, pairs);
+    const bool use_u16 = (c->kernel_mask & OSW_K_U16) != 0;
+    uint64_t launches = 0, padded = 0, rescored = 0;
+    std::vector<uint32_t> slots((size_t)c->n_dev, 0u);
+
+    // ---- phase 1: first stage on every GPU ------------------------------------------------
+    for (int i = 0; i < c->n_dev; ++i) {
+        int rc = enqueue_search(c, c->devs[i], queries, q_off, nq, matrix, go, ge, (uint32_t)top_r,
+                                all_scores != nullptr, pairs, &slots[i], &launches, &padded);
+        if (rc != OSW_OK) return rc;
+    }
+    const double t_h2d = now_ms();
+    // ---- phase 2: re-score (needs the flagged count to size nothing - only to report it) ---
+    for (int i = 0; i < c->n_dev; ++i) {
+        DevState &d = c->devs[i];
+        const osw_shard &s = d.shard;
+        const uint64_t N = s.n_seqs;
+        CK(cudaSetDevice(d.dev));
+        I32Params ip;
+        ip.stream = d.d_stream; ip.seq_off = d.d_seq_off; ip.seq_len = d.d_seq_len;
+        ip.queries = d.d_queries; ip.q_off = d.d_qoff; ip.matrix = d.d_matrix;
+        ip.n_seqs = N; ip.scores = d.d_scores; ip.scratch = d.d_scratch; ip.max_len = s.max_len ? s.max_len : 1;
+        ip.gap_open_extend = go + ge; ip.gap_extend = ge; ip.task_counter = d.d_task_counter;
+        const int i32_blocks = d.n_sms * 4;
+        if (use_u16) {
+            // the flagged count was copied to h_counts in phase 1; wait for it (tiny sync per GPU)
+            CK(cudaStreamSynchronize(d.st));
+            uint32_t n_flag = d.h_counts[0];
+            if (n_flag > d.pairs_cap) {
+                snprintf(g_err, sizeof g_err, "%u flagged pairs exceed the re-score list capacity %u", n_flag, d.pairs_cap);
+                return OSW_E_NOMEM;
+            }
+            rescored += n_flag;
+            if (n_flag) {
+                ip.pairs = d.d_pairs; ip.n_tasks = n_flag;
+                osw_launch_i32(ip, (int)std::min<uint64_t>((uint64_t)i32_blocks, ((uint64_t)n_flag + 7) / 8), d.st);
+                ++launches;
+            }
+        } else if (N) {
+            ip.pairs = nullptr; ip.n_tasks = (uint64_t)nq * N;
+            rescored += ip.n_tasks;
+            osw_launch_i32(ip, i32_blocks, d.st);
+            ++launches;
+        }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(d.ev[2], d.st));
+        const uint32_t r = (uint32_t)std::min<uint64_t>((uint64_t)top_r, N);
+        if (r) launches += osw_topr_select(d.d_scores, d.d_canon, N, nq, r, d.topr, d.st);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(d.ev[3], d.st));
+        if (r) CK(cudaMemcpyAsync(d.h_keys, d.topr.out_keys, (size_t)nq * r * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.st));
+        if (all_scores && N) CK(cudaMemcpyAsync(d.h_scores, d.d_scores, (size_t)nq * N * sizeof(int32_t), cudaMemcpyDeviceToHost, d.st));
+        if (slots[i]) CK(cudaMemcpyAsync(d.h_cycles, d.d_cycles, slots[i] * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.st));
+    }
+    // ---- phase 3: wait, order, merge ---------------------------------------------------------
+    osw_timing tm;
+    memset(&tm, 0, sizeof tm);
+    std::vector<std::vector<osw_hit>> per_dev((size_t)c->n_dev);
+    for (int i = 0; i < c->n_dev; ++i) {
+        DevState &d = c->devs[i];
+        const uint64_t N = d.shard.n_seqs;
+        CK(cudaSetDevice(d.dev));
+        CK(cudaStreamSynchronize(d.st));
+        float ms_total = 0, ms_score = 0, ms_resc = 0, ms_top = 0;
+        CK(cudaEventElapsedTime(&ms_total, d.ev[0], d.ev[3]));
+        CK(cudaEventElapsedTime(&ms_score, d.ev[0], d.ev[1]));
+        CK(cudaEventElapsedTime(&ms_resc, d.ev[1], d.ev[2]));
+        CK(cudaEventElapsedTime(&ms_top, d.ev[2], d.ev[3]));
+        tm.device_ms = std::max(tm.device_ms, (double)ms_total);
+        tm.score_ms = std::max(tm.score_ms, (double)ms_score);
+        tm.rescore_ms = std::max(tm.rescore_ms, (double)ms_resc);
+        tm.topr_ms = std::max(tm.topr_ms, (double)ms_top);
+        if (i == 0) for (uint32_t k = 0; k < slots[i]; ++k) tm.sm_cycles += d.h_cycles[k];
+        const uint32_t r = (uint32_t)std::min<uint64_t>((uint64_t)top_r, N);
+        per_dev[i].resize((size_t)nq * r);
+        for (int q = 0; q < nq; ++q) {
+            unsigned long long *k = d.h_keys + (size_t)q * r;
+            std::sort(k, k + r, [](unsigned long long x, unsigned long long y) { return x > y; });
+            for (uint32_t j = 0; j < r; ++j) {
+                per_dev[i][(size_t)q * r + j].score = (int32_t)(k[j] >> 32);
+                per_dev[i][(size_t)q * r + j].index = (uint32_t)k[j];
+            }
+        }
+        if (all_scores)
+            for (int q = 0; q < nq; ++q)
+                for (uint64_t l = 0; l < N; ++l)
+                    all_scores[(size_t)q * c->n_seqs_canon + d.shard.canon[l]] = d.h_scores[(size_t)q * N + l];
+    }
+    if (top_r > 0) {
+        std::vector<const osw_hit *> lists((size_t)c->n_dev);
+        std::vector<uint32_t> counts((size_t)c->n_dev);
+        for (int q = 0; q < nq; ++q) {
+            for (int i = 0; i < c->n_dev; ++i) {
+                const uint32_t r = (uint32_t)std::min<uint64_t>((uint64_t)top_r, c->devs[i].shard.n_seqs);
+                lists[i] = per_dev[i].data() + (size_t)q * r; counts[i] = r;
+            }
+            size_t n = osw_merge_hits(lists.data(), counts.data(), c->n_dev, (uint32_t)top_r, hits + (size_t)q * top_r);
+            if (n_hits) n_hits[q] = (uint32_t)n;
+        }
+    }
+    tm.h2d_ms = t_h2d - t_wall0;
+    tm.wall_ms = now_ms() - t_wall0;
+    tm.cells = (uint64_t)q_off[nq] * c->residues_local;
+    tm.padded_cells = padded;
+    tm.rescored_pairs = rescored;
+    tm.launches = launches;
+    tm.db_stream_bytes = 0;
+    for (int i = 0; i < c->n_dev; ++i) tm.db_stream_bytes += (uint64_t)slots[i] * c->devs[i].shard.stream_bytes;
+    if (timing) *timing = tm;
+    return OSW_OK;
+}

@@ -1,0 +1,74 @@
+// osw_internal.h - shared declarations of the CUDA side (not part of the C ABI).
+#ifndef OSW_INTERNAL_H
+#define OSW_INTERNAL_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../../include/oswald_cuda.h"
+#include "../host/dbformat.h"
+
+#define OSW_SCORE_FLAGGED 0x7fffffff   // first-stage marker: pair must be re-scored at 32 bit
+
+// ---- 32-bit kernel (sw_i32.cu): exact scores; re-score of flagged pairs, or everything ----
+struct I32Params {
+    const uint8_t  *stream;      // shard column stream
+    const uint64_t *seq_off;     // [n_seqs] stream offset of each sequence
+    const uint32_t *seq_len;     // [n_seqs]
+    const uint8_t  *queries;     // residue codes, all queries back to back
+    const uint32_t *q_off;       // [nq+1]
+    const int8_t   *matrix;      // [24*32]
+    const uint2    *pairs;       // (query, local sequence) list, or nullptr = all pairs
+    uint64_t        n_tasks;     // pairs in the list, or nq*n_seqs
+    uint64_t        n_seqs;
+    int32_t        *scores;      // [nq][n_seqs]
+    int2           *scratch;     // [warps_in_grid][max_len] (H,F) of a pass's bottom row
+    uint32_t        max_len;
+    int             gap_open_extend;   // go+ge
+    int             gap_extend;
+    unsigned long long *task_counter;  // dynamic task queue
+};
+void osw_launch_i32(const I32Params &p, int n_blocks, cudaStream_t st);
+int  osw_i32_block_threads();
+
+// ---- packed 16-bit DPX kernel (sw_u16.cu) ------------------------------------------------
+struct U16Config {       // geometry of one launch: G lanes per sequence, R rows per lane
+    int G, R, passes;
+};
+struct U16Params {
+    const uint8_t   *stream;
+    const osw_chunk *chunks;     // descending-length order
+    uint32_t         n_chunks;
+    const uint8_t   *query_a;    // rows of query A / B (codes); rows >= length read as pad
+    const uint8_t   *query_b;
+    uint32_t         len_a, len_b;
+    const int8_t    *matrix;
+    int32_t         *scores_a;   // [n_seqs] rows of the score matrix for the two queries
+    int32_t         *scores_b;   // (scores_b may be nullptr when the pair has one query)
+    const uint2     *bound_in;   // [stream_bytes] (H,F) bottom row of the previous pass, or nullptr
+    uint2           *bound_out;  // [stream_bytes] bottom row of this pass, or nullptr on the last pass
+    uint32_t         row0;       // first query row of this pass
+    int              gap_open_extend, gap_extend;
+    uint32_t        *chunk_counter;
+    unsigned long long *cycle_acc;   // [2] min start / max end clock64 of the launch (GPU-wide), or nullptr
+};
+// Picks (G,R,passes) for a query length; returns padded rows.
+uint32_t osw_u16_plan(uint32_t query_len, U16Config *cfg);
+size_t   osw_u16_smem_bytes(const U16Config &cfg);
+int      osw_launch_u16(const U16Params &p, const U16Config &cfg, int n_sms, cudaStream_t st);
+
+// ---- device top-r (topr.cu) --------------------------------------------------------------
+struct TopRWork {            // per-device scratch, sized for nq_max queries
+    uint32_t *hist;          // [nq][256]
+    unsigned long long *prefix;   // [nq] key prefix found so far
+    uint32_t *remaining;     // [nq]
+    uint32_t *out_count;     // [nq]
+    unsigned long long *out_keys;  // [nq][r]
+};
+// Selects for each of nq rows the top_r largest keys (score<<32 | canonical index) into
+// w.out_keys (unordered).  Returns number of kernels launched.
+int osw_topr_select(const int32_t *scores, const uint32_t *canon, uint64_t n_seqs, int nq,
+                    uint32_t top_r, const TopRWork &w, cudaStream_t st);
+// Marks flagged scores: appends (q, seq) of every score == OSW_SCORE_FLAGGED to pairs.
+int osw_collect_flagged(const int32_t *scores, uint64_t n_seqs, int nq, uint2 *pairs,
+                        uint32_t *count, uint32_t capacity, cudaStream_t st);
+
+#endif

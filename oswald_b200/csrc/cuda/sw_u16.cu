@@ -1,0 +1,320 @@
+// sw_u16.cu - the first-stage kernel: packed 16-bit Gotoh scoring with DPX instructions.
+//
+// Takes over the role of the reference's narrow stages (8-bit HybridSearch.c:831-913, 16-bit
+// :937-1030, and the FPGA kernel device/sw.cl) - not their structure.
+//
+// Work decomposition
+//   * A launch scores ONE PAIR of queries (A in the low, B in the high 16 bits of every
+//     32-bit word) over `G*R` consecutive query rows against every database chunk.  Both
+//     halves see the same database residue, so one shared-memory read of the pair profile
+//         prof[residue][row] = (M[A[row]][residue], M[B[row]][residue])
+//     serves two cell updates and is bank-conflict free by construction (see below).
+//   * G lanes (4, 8, 16 or 32) form a systolic array over the query rows: lane t owns rows
+//     t*R .. t*R+R-1, with H(left), E of its rows in registers.  A chunk's column stream flows
+//     through the array, lane t working on column (step - t); sequences follow one another
+//     without draining the array (flags in the stream byte restart the state).
+//   * Per step a lane reads a 16-byte message {H, F of the row above, running column maximum,
+//     residue+flags}, sweeps its R rows, and writes the same message for the lane below
+//     through a per-warp shared-memory mailbox.  Lane 0 of a group reads its messages from a
+//     ring the group fills 32 columns ahead from the chunk stream (128-bit coalesced loads);
+//     when the query needs several passes (more than 32*R rows) the ring also carries the
+//     previous pass's bottom row, and the last lane stores this pass's bottom row.
+//   * The last lane of a group sees, per column, the maximum over all rows; it keeps the
+//     running maximum of the sequence and publishes it at the column flagged LAST.
+//
+// Arithmetic: unsigned 16-bit lanes with a bias B (value v is stored as v+B), so that
+//   t  = VIADDMNMX.U16x2(Hdiag, score, E)      max(Hdiag + s, E)
+//   H  = VIMNMX3.U16x2(t, F, B)                max(t, F, 0)
+//   u  = IMAD(H, 1, -(go+ge) packed)           H - (go+ge): no borrow between halves since
+//                                              H >= B >= go+ge; runs on the FMA pipe
+//   E  = VIADDMNMX.U16x2(E, -ge, u)            max(E - ge, u)
+//   F  = VIADDMNMX.U16x2(F, -ge, u)
+//   cm = VIMNMX3.U16x2(cm, H_even, H_odd)      every second row
+// i.e. 4.5 ALU-pipe + 1 FMA-pipe instructions per word = per two cell updates.  A sequence
+// whose biased maximum reaches 65504 may have wrapped and is flagged for the 32-bit kernel
+// (scores grow by at most 17 per cell, so a wrap cannot be missed).
+#include "osw_internal.h"
+
+namespace {
+
+constexpr uint32_t FLAG_THRESHOLD = 65504;      // biased maximum at/above which a pair is re-scored
+constexpr int RING = 64;                        // ring entries per group (two halves of 32)
+
+__host__ __device__ constexpr int pitch_quads(int R) { return (R / 4) | 1; }          // odd, >= R/4
+__host__ __device__ constexpr int prof_quads(int G, int R) { return (G * pitch_quads(R) + 7) / 8 * 8; }
+__host__ __device__ constexpr int prof_copies(int G) { return G == 4 ? 2 : 1; }
+__host__ __device__ constexpr size_t prof_copy_bytes(int G, int R) { return (size_t)24 * prof_quads(G, R) * 16; }
+__host__ __device__ constexpr int block_threads(int R) { return R > 36 ? 384 : 512; }
+
+__device__ __forceinline__ uint32_t imad_add(uint32_t h, uint32_t one, uint32_t c) {
+    uint32_t u;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(u) : "r"(h), "r"(one), "r"(c));
+    return u;
+}
+// mailbox / ring traffic: ordered against __syncwarp
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// profile reads: the profile is constant once built, so the compiler may schedule these freely
+__device__ __forceinline__ uint4 lds128_const(uint32_t addr) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+struct KArgs {
+    U16Params p;
+    uint32_t one;            // 1, opaque to the compiler (forces IMAD for the subtract)
+    uint32_t bias2;          // B | B<<16
+    uint32_t nge2;           // (-ge) & 0xffff, both halves
+    uint32_t ngoe_word;      // -(goe | goe<<16) as a 32-bit two's complement
+    uint32_t bias;           // B
+};
+
+template <int G, int R>
+__global__ void __launch_bounds__(block_threads(R), 1)
+sw_u16_kernel(const KArgs a) {
+    constexpr int THREADS = block_threads(R);
+    constexpr int WARPS = THREADS / 32;
+    constexpr int GROUPS = 32 / G;              // groups per warp
+    constexpr int P = pitch_quads(R);
+    constexpr int PITCH_B = prof_quads(G, R) * 16;
+    constexpr int COPY_B = (int)prof_copy_bytes(G, R);
+    constexpr int EPL = 32 / G;                 // ring entries each lane fills per 32-column block
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    // layout: [profile copies][mailbox: WARPS*32 uint4][rings: WARPS*GROUPS*RING uint4]
+    unsigned char *s_prof = smem;
+    constexpr int PROF_B = COPY_B * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0);
+    uint4 *s_mail = reinterpret_cast<uint4 *>(smem + PROF_B);
+    uint4 *s_ring = s_mail + WARPS * 32;
+    __shared__ int s_mat[24 * 32];
+    __shared__ uint32_t s_chunk[WARPS];
+
+    const U16Params &p = a.p;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int t = lane % G, grp = lane / G;
+    long long clk0 = clock64();
+
+    // ---- build the pair profile for rows row0 .. row0+G*R-1 ------------------------------
+    for (int i = threadIdx.x; i < 24 * 32; i += THREADS) s_mat[i] = p.matrix[i];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < prof_copies(G) * 24 * prof_quads(G, R); idx += THREADS) {
+        const int copy = idx / (24 * prof_quads(G, R));
+        const int rem = idx % (24 * prof_quads(G, R));
+        const int b = rem / prof_quads(G, R), slot = rem % prof_quads(G, R);
+        const int tt = slot / P, k = slot % P;
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (tt < G && k < R / 4) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t row = p.row0 + tt * R + 4 * k + r;
+                const int ca = row < p.len_a ? p.query_a[row] : OSW_PAD_CODE;
+                const int cb = row < p.len_b ? p.query_b[row] : OSW_PAD_CODE;
+                w[r] = ((uint32_t)s_mat[ca * 32 + b] & 0xffffu) | ((uint32_t)s_mat[cb * 32 + b] << 16);
+            }
+        }
+        // the second copy (G == 4) sits 64 bytes further modulo 128, i.e. 4 bank groups away
+        unsigned char *dst = s_prof + copy * (COPY_B + 64) + b * PITCH_B + slot * 16;
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __syncthreads();
+
+    const uint32_t prof_lane = (uint32_t)__cvta_generic_to_shared(s_prof) +
+                               (prof_copies(G) > 1 ? (grp & 1) * (COPY_B + 64) : 0) + t * P * 16;
+    const uint32_t mail_self = (uint32_t)__cvta_generic_to_shared(s_mail + wib * 32 + lane);
+    const uint32_t mail_up = mail_self - 16;     // lane-1's mailbox (unused when t == 0)
+    const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(s_ring + (wib * GROUPS + grp) * RING);
+    const uint32_t B2 = a.bias2, NGE = a.nge2, NGOE = a.ngoe_word, ONE = a.one;
+    const bool multi_in = p.bound_in != nullptr;
+
+    for (;;) {
+        // ---- fetch one chunk per group ---------------------------------------------------
+        if (lane == 0) s_chunk[wib] = atomicAdd(p.chunk_counter, (uint32_t)GROUPS);
+        __syncwarp();
+        const uint32_t cbase = s_chunk[wib];
+        __syncwarp();
+        if (cbase >= p.n_chunks) break;
+        const uint32_t ci = cbase + grp;
+        const bool have = ci < p.n_chunks;
+        osw_chunk ck;
+        if (have) ck = p.chunks[ci]; else { ck.stream_off = 0; ck.n_cols = 0; ck.n_seqs = 0; ck.seq0 = 0; ck.canon0 = 0; }
+        uint32_t steps = have ? ck.n_cols + G - 1 : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+        const uint32_t n_blocks = (steps + 31) / 32;
+        const uint8_t *col_src = p.stream + ck.stream_off + t * EPL;
+        const uint2 *bnd_src = multi_in ? p.bound_in + ck.stream_off + t * EPL : nullptr;
+        const uint32_t cols_padded = have ? (ck.n_cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN : 0;
+
+        // ring fill helpers: block b covers columns [32b, 32b+32); this lane fills EPL of them
+        uint32_t pre_cols[2];            // up to 8 stream bytes
+        uint2 pre_bnd;                   // (G == 32 only: EPL == 1)
+        auto prefetch = [&](uint32_t b) {
+            pre_cols[0] = pre_cols[1] = 0x17171717u;     // pad residues
+            pre_bnd = make_uint2(B2, B2);
+            if (32 * b < cols_padded) {
+                const uint8_t *src = col_src + 32 * b;
+                if (EPL == 8) { uint2 v = __ldg(reinterpret_cast<const uint2 *>(src)); pre_cols[0] = v.x; pre_cols[1] = v.y; }
+                else if (EPL == 4) pre_cols[0] = __ldg(reinterpret_cast<const uint32_t *>(src));
+                else if (EPL == 2) pre_cols[0] = __ldg(reinterpret_cast<const uint16_t *>(src));
+                else pre_cols[0] = __ldg(src);
+                if (EPL == 1 && multi_in) pre_bnd = __ldcg(bnd_src + 32 * b);
+            }
+        };
+        auto commit = [&](uint32_t b) {
+            const uint32_t dst = ring_base + ((b & 1) * 32 + t * EPL) * 16;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) {
+                const uint32_t byte = (pre_cols[e >> 2] >> (8 * (e & 3))) & 0xffu;
+                sts128(dst + e * 16, make_uint4(pre_bnd.x, pre_bnd.y, B2, byte));
+            }
+        };
+        prefetch(0);
+        commit(0);
+
+        uint32_t Hl[R], E[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { Hl[r] = B2; E[r] = B2; }
+        uint32_t diag_top = B2, run = B2;
+        uint32_t seq = ck.seq0;
+        sts128(mail_self, make_uint4(B2, B2, B2, OSW_COL_PADBYTE));
+        __syncwarp();
+
+        for (uint32_t blk = 0; blk < n_blocks; ++blk) {
+            prefetch(blk + 1);
+#pragma unroll 1
+            for (uint32_t i = 0; i < 32; ++i) {
+                const uint32_t step = blk * 32 + i;
+                const uint32_t in_addr = t == 0 ? ring_base + (step & (RING - 1)) * 16 : mail_up;
+                const uint4 in = lds128(in_addr);
+                const uint32_t lf = in.w;
+                if (lf & OSW_COL_FIRST) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) { Hl[r] = B2; E[r] = B2; }
+                    diag_top = B2;
+                }
+                const uint32_t paddr = prof_lane + (lf & OSW_COL_CODE) * PITCH_B;
+                uint32_t F = in.y, diag = diag_top, cm = in.z, Heven = B2;
+#pragma unroll
+                for (int k = 0; k < R / 4; ++k) {
+                    const uint4 sv = lds128_const(paddr + k * 16);
+                    const uint32_t sc[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int r = 4 * k + rr;
+                        const uint32_t tt = __viaddmax_u16x2(diag, sc[rr], E[r]);
+                        const uint32_t H = __vimax3_u16x2(tt, F, B2);
+                        const uint32_t u = imad_add(H, ONE, NGOE);
+                        E[r] = __viaddmax_u16x2(E[r], NGE, u);
+                        F = __viaddmax_u16x2(F, NGE, u);
+                        diag = Hl[r];
+                        Hl[r] = H;
+                        if (rr & 1) cm = __vimax3_u16x2(cm, Heven, H); else Heven = H;
+                    }
+                }
+                diag_top = in.x;
+                run = __vmaxu2(run, cm);
+                if (t == G - 1) {
+                    // column index of this lane in the chunk: step - t
+                    const uint32_t col = step - (G - 1);
+                    if (p.bound_out && col < cols_padded)
+                        __stcg(p.bound_out + ck.stream_off + col, make_uint2(Hl[R - 1], F));
+                    if (lf & OSW_COL_LAST) {
+                        const uint32_t lo = run & 0xffffu, hi = run >> 16;
+                        const int sa = lo >= FLAG_THRESHOLD ? OSW_SCORE_FLAGGED : (int)(lo - a.bias);
+                        const int sb = hi >= FLAG_THRESHOLD ? OSW_SCORE_FLAGGED : (int)(hi - a.bias);
+                        atomicMax(p.scores_a + seq, sa);
+                        if (p.scores_b) atomicMax(p.scores_b + seq, sb);
+                        ++seq;
+                        run = B2;
+                    }
+                }
+                __syncwarp();
+                sts128(mail_self, make_uint4(Hl[R - 1], F, cm, lf));
+                __syncwarp();
+            }
+            commit(blk + 1);
+            __syncwarp();
+        }
+    }
+    if (p.cycle_acc && threadIdx.x == 0) atomicMax(p.cycle_acc, (unsigned long long)(clock64() - clk0));
+}
+
+template <int G, int R>
+int launch_one(const KArgs &a, int n_sms, cudaStream_t st) {
+    constexpr int THREADS = block_threads(R);
+    const size_t prof = prof_copy_bytes(G, R) * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0);
+    const size_t smem = prof + (size_t)(THREADS / 32) * 32 * 16 + (size_t)(THREADS / 32) * (32 / G) * RING * 16;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(sw_u16_kernel<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return OSW_E_CUDA;
+        configured = true;
+    }
+    sw_u16_kernel<G, R><<<n_sms, THREADS, smem, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? OSW_OK : OSW_E_CUDA;
+}
+
+template <int G>
+int launch_g(int R, const KArgs &a, int n_sms, cudaStream_t st) {
+    switch (R) {
+        case 16: return launch_one<G, 16>(a, n_sms, st);
+        case 20: return launch_one<G, 20>(a, n_sms, st);
+        case 24: return launch_one<G, 24>(a, n_sms, st);
+        case 28: return launch_one<G, 28>(a, n_sms, st);
+        case 32: return launch_one<G, 32>(a, n_sms, st);
+        case 36: return launch_one<G, 36>(a, n_sms, st);
+        case 40: return launch_one<G, 40>(a, n_sms, st);
+        case 44: return launch_one<G, 44>(a, n_sms, st);
+    }
+    return OSW_E_ARG;
+}
+
+}  // namespace
+
+// Geometry for a query of `query_len` rows: minimise passes*G*(R+3) (3 = per-column overhead
+// in row equivalents) subject to passes*G*R >= query_len; several passes only with G = 32.
+uint32_t osw_u16_plan(uint32_t query_len, U16Config *cfg) {
+    static const int Gs[4] = {4, 8, 16, 32};
+    static const int Rs[8] = {16, 20, 24, 28, 32, 36, 40, 44};
+    uint64_t best_cost = ~0ull;
+    U16Config best = {32, 44, 1};
+    if (query_len == 0) query_len = 1;
+    for (int gi = 0; gi < 4; ++gi)
+        for (int ri = 0; ri < 8; ++ri) {
+            const int G = Gs[gi], R = Rs[ri];
+            uint32_t passes = (query_len + G * R - 1) / (G * R);
+            if (passes > 1 && G != 32) continue;
+            uint64_t cost = (uint64_t)passes * G * (R + 3);
+            if (cost < best_cost || (cost == best_cost && (int)passes < best.passes)) {
+                best_cost = cost; best.G = G; best.R = R; best.passes = (int)passes;
+            }
+        }
+    *cfg = best;
+    return (uint32_t)(best.passes * best.G * best.R);
+}
+
+int osw_launch_u16(const U16Params &p, const U16Config &cfg, int n_sms, cudaStream_t st) {
+    KArgs a;
+    a.p = p;
+    a.one = 1u;
+    const uint32_t goe = (uint32_t)p.gap_open_extend, ge = (uint32_t)p.gap_extend;
+    const uint32_t B = goe + ge + 32u;
+    a.bias = B; a.bias2 = B | (B << 16);
+    const uint32_t nge = (0x10000u - ge) & 0xffffu;
+    a.nge2 = nge | (nge << 16);
+    a.ngoe_word = 0u - (goe | (goe << 16));
+    switch (cfg.G) {
+        case 4:  return launch_g<4>(cfg.R, a, n_sms, st);
+        case 8:  return launch_g<8>(cfg.R, a, n_sms, st);
+        case 16: return launch_g<16>(cfg.R, a, n_sms, st);
+        case 32: return launch_g<32>(cfg.R, a, n_sms, st);
+    }
+    return OSW_E_ARG;
+}

@@ -1,0 +1,67 @@
+/* dbformat.h - the GPU database layout: length-binned chunk streams.
+ *
+ * Replaces the reference's 32-lane interleaved groups (assemble_db_chunks, reference
+ * sequences.c:1035-1088) and its measured-GCUPS FPGA/host split (sequences.c:842-863).
+ *
+ * The canonical database (stable ascending length order, sequences.c:1130-1225) is cut into
+ * CHUNKS of consecutive whole sequences holding about `chunk_cols` residues each (one longer
+ * sequence is a chunk of its own).  Because the order is by length, a chunk is a length bin:
+ * all its sequences have (nearly) the same length.  A chunk is stored as a COLUMN STREAM, one
+ * byte per residue:
+ *      bits 0-4  residue code 0..23
+ *      bit  5    OSW_COL_FIRST  first column of a sequence (DP state restarts here)
+ *      bit  6    OSW_COL_LAST   last column of a sequence (its score is complete here)
+ * Chunk streams start on 128-byte boundaries (padding bytes are OSW_COL_PADBYTE), so a warp reads a
+ * stream with coalesced 128-bit loads.  Chunk c of the database is dealt to shard
+ * (c mod n_shards): every shard gets the same mix of lengths and the same number of
+ * residues to within one chunk - the residue-balanced split across GPUs.
+ */
+#ifndef OSW_DBFORMAT_H
+#define OSW_DBFORMAT_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSW_COL_CODE  0x1f
+#define OSW_COL_FIRST 0x20
+#define OSW_COL_LAST  0x40
+#define OSW_COL_PADBYTE 23           /* pad residue, no flags */
+#define OSW_CHUNK_ALIGN 128
+#define OSW_CHUNK_COLS_DEFAULT 4096
+
+typedef struct osw_chunk {
+    uint64_t stream_off;   /* byte offset of the first column in the shard stream */
+    uint32_t n_cols;       /* residues in the chunk */
+    uint32_t n_seqs;       /* whole sequences in the chunk */
+    uint32_t seq0;         /* shard-local index of its first sequence */
+    uint32_t canon0;       /* canonical index of its first sequence (the rest follow) */
+} osw_chunk;
+
+typedef struct osw_shard {
+    uint64_t   n_seqs;         /* sequences in this shard */
+    uint64_t   n_residues;     /* residues in this shard */
+    uint64_t   stream_bytes;   /* size of stream (multiple of OSW_CHUNK_ALIGN) */
+    uint32_t   n_chunks;
+    uint32_t   max_len;        /* longest sequence in the shard */
+    uint8_t   *stream;         /* column stream, chunks back to back */
+    osw_chunk *chunks;         /* in DESCENDING length order (longest work is handed out first) */
+    uint32_t  *canon;          /* canon[local] = canonical index */
+    uint64_t  *seq_off;        /* seq_off[local] = stream offset of the sequence's first column */
+    uint32_t  *seq_len;        /* seq_len[local] */
+} osw_shard;
+
+/* Number of chunks the whole canonical database is cut into. */
+uint64_t osw_count_chunks(const uint64_t *offsets, uint64_t n_seqs, uint32_t chunk_cols);
+
+/* Build shard `shard` of `n_shards` (chunk c belongs to shard c mod n_shards).
+ * Returns 0, or -1 on allocation failure / bad arguments. */
+int osw_shard_build(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
+                    uint32_t shard, uint32_t n_shards, uint32_t chunk_cols, osw_shard *out);
+void osw_shard_free(osw_shard *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -113,6 +113,15 @@ def read_fasta(path):
     return titles, seqs
 
 
+def read_fasta_gz(path):
+    import gzip, shutil, tempfile
+    with tempfile.NamedTemporaryFile(suffix=".fasta") as tmp:
+        with gzip.open(path, "rb") as g:
+            shutil.copyfileobj(g, tmp)
+        tmp.flush()
+        return read_fasta(tmp.name)
+
+
 def canonical(titles, seqs):
     """Reference preprocessing: stable ascending length sort, encode, concatenate."""
     lens = np.array([len(s) for s in seqs], dtype=np.uint32)

@@ -1,0 +1,195 @@
+"""GPU parity tests (B200): every score and every top-r list through the C ABI must equal the
+reference's own output (golden fixtures) and the oracle, bit for bit."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from golden_util import CASES, load_case
+import oswald_b200 as ob
+from oswald_b200 import capi
+
+pytestmark = pytest.mark.gpu
+AA = np.array([0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 21], dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def searcher(built):
+    s = ob.Searcher(1)
+    yield s
+    s.close()
+
+
+def rand_seqs(rng, n, lo, hi):
+    return [AA[rng.integers(0, 20, size=int(l))] for l in rng.integers(lo, hi, size=n)]
+
+
+def make_db(seqs):
+    lens = np.array([len(s) for s in seqs], dtype=np.uint64)
+    return ob.Database.from_lengths(lens, np.concatenate(seqs) if len(seqs) else np.zeros(0, np.uint8))
+
+
+def oracle_scores(q, db, name, go, ge):
+    return O.search(q.residues, q.offsets, db.residues, db.offsets, O.matrix(name), go, ge)
+
+
+def check(searcher, db, q, name, go, ge, top, mask=capi.OSW_K_DEFAULT, want=None):
+    searcher.set_kernels(mask)
+    hits, tm, scores = searcher.search(q, ob.matrix(name), go, ge, top=top, all_scores=True)
+    if want is None:
+        want = oracle_scores(q, db, name, go, ge)
+    bad = np.argwhere(scores != want)
+    assert bad.size == 0, "first mismatches (query, index): %s got %s want %s" % (
+        bad[:5].tolist(), scores[tuple(bad[:5].T)].tolist(), want[tuple(bad[:5].T)].tolist())
+    for qi in range(q.n):
+        idx, sc = O.top_r(want[qi], top)
+        assert hits[qi] == [(int(s), int(i)) for s, i in zip(sc, idx)], "top-r of query %d" % qi
+    return tm
+
+
+@pytest.mark.parametrize("mask", [capi.OSW_K_I32, capi.OSW_K_DEFAULT])
+@pytest.mark.parametrize("name", CASES)
+def test_golden_cases(searcher, name, mask):
+    """Score matrices and printed top-r lists of the reference's host AVX2 path."""
+    meta = load_case(name)
+    db = ob.preprocess_db(meta["db_fasta"])
+    q = ob.load_query_sequences(meta["q_fasta"])
+    searcher.load_db(db)
+    searcher.set_kernels(mask)
+    for run in meta["runs"]:
+        hits, tm, scores = searcher.search(q, ob.matrix(run["matrix"]), run["gap_open"], run["gap_extend"],
+                                           top=meta["top"], all_scores=True)
+        assert np.array_equal(scores, run["score_matrix"]), (name, run["matrix"])
+        for qi, h in enumerate(run["hits"]):
+            got = [[s, db.titles[i]] for s, i in hits[qi]]
+            assert got == h["top"], (name, run["matrix"], qi)
+        if name == "g2_overflow" and mask == capi.OSW_K_DEFAULT:
+            assert tm["rescored_pairs"] > 0          # the tandem repeat exceeds 16 bits
+            assert tm["rescored_pairs"] < 64
+
+
+@pytest.mark.parametrize("lengths", [[144], [5, 37, 144, 189], [1, 1, 2], [144, 189, 222, 375, 464, 567, 657],
+                                      [1000, 1500], [2005], [1537, 3005]])
+def test_random_db_all_query_geometries(searcher, lengths):
+    """Every (G, R, passes) plan the query lengths select, odd and even query counts."""
+    rng = np.random.default_rng(sum(lengths))
+    seqs = rand_seqs(rng, 700, 1, 500)
+    q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in lengths])
+    seqs[3] = q.query(q.n - 1).copy()                                  # an exact copy of the longest query
+    seqs[5] = np.concatenate([q.query(0), rng.permutation(q.query(q.n - 1))])
+    db = make_db(seqs)
+    searcher.load_db(db)
+    check(searcher, db, q, "blosum62", 10, 2, 10)
+
+
+@pytest.mark.parametrize("name,go,ge", [("blosum45", 14, 2), ("blosum50", 10, 2), ("blosum80", 10, 2), ("blosum90", 10, 2),
+                                        ("pam30", 9, 1), ("pam70", 10, 1), ("pam250", 12, 2), ("blosum62", 0, 0),
+                                        ("blosum62", 255, 127), ("blosum62", 1, 0)])
+def test_matrices_and_gap_penalties(searcher, name, go, ge):
+    rng = np.random.default_rng(go * 131 + ge)
+    seqs = rand_seqs(rng, 400, 1, 300)
+    q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (60, 144, 333)])
+    for k in range(6):                                                  # homologs with indels
+        src = q.query(k % 3)
+        cut = rng.integers(1, len(src))
+        seqs[k] = np.concatenate([src[:cut], AA[rng.integers(0, 20, size=rng.integers(0, 6))], src[cut:]])
+    db = make_db(seqs)
+    searcher.load_db(db)
+    check(searcher, db, q, name, go, ge, 15)
+
+
+def test_edge_shapes(searcher):
+    rng = np.random.default_rng(9)
+    # single sequence, single residue; database smaller than top; sequences of length 1
+    q = ob.Queries.from_list([AA[rng.integers(0, 20, size=50)]])
+    for seqs in ([AA[:1]], [AA[:1], AA[3:4], AA[5:9]], rand_seqs(rng, 33, 1, 3)):
+        db = make_db(seqs)
+        searcher.load_db(db)
+        check(searcher, db, q, "blosum62", 10, 2, 10)
+    # residues outside the 20 standard ones (B, X, Z and the J/O/U code 23) in the database
+    seqs = [rng.integers(0, 24, size=int(l)).astype(np.uint8) for l in rng.integers(1, 200, size=300)]
+    db = make_db(seqs)
+    searcher.load_db(db)
+    check(searcher, db, ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (77, 200)]), "blosum62", 10, 2, 5)
+
+
+def test_all_ties_rank_by_higher_index(searcher):
+    seq = AA[[0, 1, 2, 3, 4, 5, 6, 7]]
+    db = make_db([seq.copy() for _ in range(500)])
+    searcher.load_db(db)
+    q = ob.Queries.from_list([seq])
+    hits, tm = searcher.search(q, ob.matrix("blosum62"), 10, 2, top=7)
+    assert [i for _, i in hits[0]] == [499, 498, 497, 496, 495, 494, 493]
+    assert len({s for s, _ in hits[0]}) == 1
+
+
+def test_long_sequences_and_chunk_boundaries(searcher):
+    """Sequences longer than a chunk (incl. the u16 maximum 65535) and tiny chunks."""
+    rng = np.random.default_rng(21)
+    q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (144, 464)])
+    seqs = rand_seqs(rng, 200, 1, 200) + [AA[rng.integers(0, 20, size=n)] for n in (4095, 4096, 4097, 9000, 36000, 65535)]
+    seqs[-2][1000:1464] = q.query(1)
+    db = make_db(seqs)
+    want = oracle_scores(q, db, "blosum62", 10, 2)
+    for k in (0, 64, 300):
+        searcher.load_db(db, max_chunk_residues=k)
+        check(searcher, db, q, "blosum62", 10, 2, 10, want=want)
+
+
+def test_overflow_rescore_exact(searcher):
+    """Scores beyond 16 bits: tandem copies of a long query (PAM30) must come back exact."""
+    rng = np.random.default_rng(4)
+    long_q = AA[rng.integers(0, 20, size=5478)]
+    q = ob.Queries.from_list([AA[rng.integers(0, 20, size=144)], long_q])
+    seqs = rand_seqs(rng, 100, 50, 400) + [np.concatenate([long_q] * 3), np.concatenate([long_q] * 2 + [AA[:7]]), long_q.copy()]
+    db = make_db(seqs)
+    searcher.load_db(db)
+    tm = check(searcher, db, q, "pam30", 9, 1, 10)
+    assert 1 <= tm["rescored_pairs"] <= 4
+    want = oracle_scores(q, db, "pam30", 9, 1)
+    assert want.max() > 65535
+
+
+def test_sharded_contexts_merge_to_the_same_hits(built):
+    """Two shards (as two ranks would hold them) merged on the host == one unsharded search."""
+    from oswald_b200.host import merge_hits
+    rng = np.random.default_rng(77)
+    db = make_db(rand_seqs(rng, 3000, 20, 300))
+    q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (100, 200, 300)])
+    want = oracle_scores(q, db, "blosum62", 10, 2)
+    parts, all_scores = [], np.zeros_like(want)
+    for rank in range(2):
+        with ob.Searcher(1) as s:
+            s.load_db(db, shard_rank=rank, shard_count=2, max_chunk_residues=512)
+            st = s.stats()
+            assert abs(st["residues"] - db.n_residues / 2) < 0.02 * db.n_residues
+            hits, tm, sc = s.search(q, ob.matrix("blosum62"), 10, 2, top=10, all_scores=True)
+            parts.append(hits)
+            all_scores += sc            # untouched entries stay 0
+    assert np.array_equal(all_scores, want)
+    for qi in range(q.n):
+        idx, sc = O.top_r(want[qi], 10)
+        assert merge_hits([parts[0][qi], parts[1][qi]], 10) == [(int(s), int(i)) for s, i in zip(sc, idx)]
+
+
+def test_swissprot_shape_properties(searcher):
+    """A slice of the Swiss-Prot-shaped workload too big for the scalar oracle: the packed
+    16-bit kernel and the 32-bit kernel (different code, different geometry) must agree on every
+    score, and planted exact copies must score their self-score."""
+    rng = np.random.default_rng(123)
+    lens = np.clip(np.round(np.exp(rng.normal(5.6, 0.6, size=20000))), 10, 5000).astype(np.uint64)
+    seqs = [AA[rng.integers(0, 20, size=int(l))] for l in lens]
+    qs = [AA[rng.integers(0, 20, size=m)] for m in (144, 375, 1000, 2005)]
+    for k, qq in enumerate(qs):
+        seqs[100 + k] = qq.copy()
+    db = make_db(seqs)
+    q = ob.Queries.from_list(qs)
+    searcher.load_db(db)
+    searcher.set_kernels(capi.OSW_K_DEFAULT)
+    h1, tm1, s1 = searcher.search(q, ob.matrix("blosum62"), 10, 2, top=10, all_scores=True)
+    searcher.set_kernels(capi.OSW_K_I32)
+    h2, tm2, s2 = searcher.search(q, ob.matrix("blosum62"), 10, 2, top=10, all_scores=True)
+    assert np.array_equal(s1, s2) and h1 == h2
+    m = ob.matrix("blosum62").reshape(24, 32)
+    for k in range(q.n):
+        self_score = int(sum(m[c, c] for c in q.query(k)))
+        assert h1[k][0][0] == self_score

@@ -1,0 +1,152 @@
+"""CPU tests of the host side: the C ABI library loads and exports what include/*.h declares,
+the chunk-stream builder, the host mirror (preprocess / query loading), hit merging, and the
+executable model of the 16-bit kernel's dataflow against the oracle.  No GPU calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import emu_u16
+from golden_util import load_case
+import oswald_b200 as ob
+from oswald_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+AA = np.array([0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 21], dtype=np.uint8)
+
+
+def test_library_exports_every_declared_symbol(built):
+    header = open(os.path.join(ROOT, "include", "oswald_cuda.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b(osw_[a-z0-9_]+)\s*\(", header))
+    assert names == set(capi.SYMBOLS), names ^ set(capi.SYMBOLS)
+    for n in names:
+        assert hasattr(built, n), n
+
+
+def test_no_device_is_an_error_not_a_fallback(built):
+    n = C.c_int(-1)
+    rc = built.osw_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.OswError):
+        ob.Searcher(1)
+
+
+class Chunk(C.Structure):
+    _fields_ = [("stream_off", C.c_uint64), ("n_cols", C.c_uint32), ("n_seqs", C.c_uint32),
+                ("seq0", C.c_uint32), ("canon0", C.c_uint32)]
+
+
+class Shard(C.Structure):
+    _fields_ = [("n_seqs", C.c_uint64), ("n_residues", C.c_uint64), ("stream_bytes", C.c_uint64),
+                ("n_chunks", C.c_uint32), ("max_len", C.c_uint32), ("stream", C.POINTER(C.c_uint8)),
+                ("chunks", C.POINTER(Chunk)), ("canon", C.POINTER(C.c_uint32)),
+                ("seq_off", C.POINTER(C.c_uint64)), ("seq_len", C.POINTER(C.c_uint32))]
+
+
+def build_shard(L, db, shard, n_shards, chunk_cols):
+    L.osw_shard_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Shard)]
+    L.osw_shard_build.restype = C.c_int
+    s = Shard()
+    assert L.osw_shard_build(db.residues.ctypes.data, db.offsets.ctypes.data, db.n_seqs, shard, n_shards, chunk_cols, C.byref(s)) == 0
+    return s
+
+
+def random_db(rng, n, lo=1, hi=300):
+    lens = rng.integers(lo, hi, size=n).astype(np.uint64)
+    res = AA[rng.integers(0, 20, size=int(lens.sum()))]
+    return ob.Database.from_lengths(lens, res)
+
+
+@pytest.mark.parametrize("n_shards", [1, 2, 8])
+def test_chunk_streams(built, n_shards):
+    rng = np.random.default_rng(11)
+    db = random_db(rng, 3000)
+    lens = np.diff(db.offsets.astype(np.int64))
+    assert np.all(lens[1:] >= lens[:-1])
+    seen = np.zeros(db.n_seqs, dtype=int)
+    residues = []
+    for sh in range(n_shards):
+        s = build_shard(built, db, sh, n_shards, 1024)
+        stream = np.ctypeslib.as_array(s.stream, shape=(s.stream_bytes,))
+        assert s.stream_bytes % 128 == 0
+        residues.append(s.n_residues)
+        prev_len = None
+        for c in range(s.n_chunks):
+            ck = s.chunks[c]
+            assert ck.stream_off % 128 == 0
+            first_len = s.seq_len[ck.seq0 + ck.n_seqs - 1]
+            if prev_len is not None:
+                assert first_len <= prev_len          # descending length order of chunks
+            prev_len = first_len
+            pos = ck.stream_off
+            for k in range(ck.n_seqs):
+                l = ck.seq0 + k
+                canon = s.canon[l]
+                assert canon == ck.canon0 + k
+                seen[canon] += 1
+                n = s.seq_len[l]
+                assert s.seq_off[l] == pos and n == lens[canon]
+                col = stream[pos:pos + n]
+                assert np.array_equal(col & 31, db.sequence(canon))
+                flags = col >> 5
+                want = np.zeros(n, dtype=np.uint8)
+                want[0] |= 1
+                want[-1] |= 2
+                assert np.array_equal(flags, want)
+                pos += n
+            assert pos - ck.stream_off == ck.n_cols
+            pad_end = ck.stream_off + (ck.n_cols + 127) // 128 * 128
+            assert np.all(stream[pos:pad_end] == 23)
+        built.osw_shard_free(C.byref(s))
+    assert np.all(seen == 1)                           # every sequence in exactly one shard
+    if n_shards > 1:
+        assert max(residues) - min(residues) <= 2 * 1024 + int(lens.max())     # residue-balanced
+
+
+def test_host_mirror_matches_reference_preprocessing():
+    meta = load_case("g3_kat")
+    db = ob.preprocess_db(meta["db_fasta"])
+    assert db.titles == meta["desc"]                    # the reference's own .desc order
+    titles, seqs = O.read_fasta_gz(meta["db_fasta"])
+    _, codes, off = O.canonical(titles, seqs)
+    assert np.array_equal(db.residues, codes) and np.array_equal(db.offsets, off)
+    q = ob.load_query_sequences(meta["q_fasta"])
+    assert list(q.lengths()) == sorted(q.lengths())
+    assert [h["query_length"] for h in meta["runs"][0]["hits"]] == list(q.lengths())
+
+
+def test_merge_hits_reference_order(built):
+    rng = np.random.default_rng(2)
+    scores = rng.integers(0, 9, size=500).astype(np.int32)
+    parts = [np.arange(k, 500, 3) for k in range(3)]
+    lists = []
+    for p in parts:
+        idx, sc = O.top_r(scores[p], 20)
+        lists.append([(int(s), int(p[i])) for s, i in zip(sc, idx)])
+    from oswald_b200.host import merge_hits
+    got = merge_hits(lists, 20)
+    idx, sc = O.top_r(scores, 20)
+    assert got == [(int(s), int(i)) for s, i in zip(sc, idx)]
+    assert merge_hits([[], [(3, 1)]], 5) == [(3, 1)]
+
+
+@pytest.mark.parametrize("G,R", [(1, 4), (2, 8), (4, 4), (4, 12)])
+def test_u16_dataflow_model_matches_oracle(G, R):
+    """The systolic/biased-unsigned scheme of sw_u16.cu, modelled step by step in Python."""
+    rng = np.random.default_rng(100 + G * R)
+    for trial in range(12):
+        name = ["blosum62", "pam30", "blosum45", "pam250"][trial % 4]
+        go, ge = [(10, 2), (9, 1), (14, 2), (0, 0), (255, 127)][trial % 5]
+        mat = O.matrix(name)
+        seqs = [AA[rng.integers(0, 20, size=rng.integers(1, 30))] for _ in range(rng.integers(1, 6))]
+        q = AA[rng.integers(0, 20, size=int(rng.integers(1, 3 * G * R)))]
+        if trial % 3 == 0:
+            seqs[0] = np.concatenate([q[:len(q) // 2 + 1], seqs[0]])
+        got = emu_u16.score_chunk(seqs, list(q), G, R, mat, go, ge)
+        want = np.array([O.sw_score(q, s, mat, go, ge) for s in seqs])
+        assert np.array_equal(got, want)
