@@ -1,0 +1,127 @@
+/* preprocess.c - `-O preprocess`: FASTA -> X.info / X.seq / X.desc, byte-compatible with the
+ * reference (sequences.c:4-220):
+ *   X.info  ASCII "N D max_title_length"            (:187; title length = line incl. '>' and
+ *                                                     '\n', plus one, :35)
+ *   X.seq   N little-endian u16 lengths (ascending), then D residue codes in that order (:202-205)
+ *   X.desc  N lines ">title", in that order          (:137-138)
+ * and the loader of that triple for `-O search`. */
+#include "oswald_host.h"
+#include <fcntl.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+int preprocess_db(const char *input_filename, const char *out_filename, int n_procs) {
+    (void)n_procs;
+    osw_fasta fa;
+    int rc = osw_fasta_read(input_filename, &fa);
+    if (rc == -1) { printf("OSWALD: An error occurred while opening input sequence file.\n"); return 2; }
+    if (rc) { printf("OSWALD: An error occurred while allocating memory for sequences.\n"); return 1; }
+    for (uint64_t i = 0; i < fa.n; ++i)
+        if (fa.offsets[i + 1] - fa.offsets[i] > 65535) {
+            printf("OSWALD: sequence %lu is longer than 65535 residues (lengths are 16-bit in the database format).\n", (unsigned long)i + 1);
+            osw_fasta_free(&fa);
+            return 1;
+        }
+    uint64_t *perm = osw_length_order(&fa);
+    if (!perm) { printf("OSWALD: An error occurred while allocating memory.\n"); osw_fasta_free(&fa); return 1; }
+    char filename[4096];
+    snprintf(filename, sizeof filename, "%s.desc", out_filename);
+    FILE *titles_file = fopen(filename, "w");
+    if (!titles_file) { printf("OSWALD: An error occurred while opening sequence header file.\n"); return 2; }
+    int max_title_length = 0;
+    for (uint64_t k = 0; k < fa.n; ++k) {
+        const char *t = fa.titles[perm[k]];
+        int tl = (int)strlen(t) + 3;                     /* '>' + title + '\n', plus one */
+        if (tl > max_title_length) max_title_length = tl;
+        fputc('>', titles_file); fputs(t, titles_file); fputc('\n', titles_file);
+    }
+    fclose(titles_file);
+    snprintf(filename, sizeof filename, "%s.info", out_filename);
+    FILE *info_file = fopen(filename, "w");
+    if (!info_file) { printf("OSWALD: An error occurred while opening info file.\n"); return 2; }
+    fprintf(info_file, "%ld %ld %d", (long)fa.n, (long)fa.n_residues, max_title_length);
+    fclose(info_file);
+    snprintf(filename, sizeof filename, "%s.seq", out_filename);
+    FILE *bin_file = fopen(filename, "wb");
+    if (!bin_file) { printf("OSWALD: An error occurred while opening sequence file.\n"); return 2; }
+    uint16_t *lens = (uint16_t *)malloc((fa.n ? fa.n : 1) * sizeof(uint16_t));
+    for (uint64_t k = 0; k < fa.n; ++k) lens[k] = (uint16_t)(fa.offsets[perm[k] + 1] - fa.offsets[perm[k]]);
+    fwrite(lens, sizeof(uint16_t), fa.n, bin_file);
+    for (uint64_t k = 0; k < fa.n; ++k) fwrite(fa.residues + fa.offsets[perm[k]], 1, lens[k], bin_file);
+    fclose(bin_file);
+    free(lens); free(perm);
+    osw_fasta_free(&fa);
+    return 0;
+}
+
+int load_database(const char *prefix, osw_database *db) {
+    memset(db, 0, sizeof *db);
+    char filename[4096];
+    snprintf(filename, sizeof filename, "%s.info", prefix);
+    FILE *info = fopen(filename, "r");
+    if (!info) { printf("OSWALD: An error occurred while opening info file.\n"); return 2; }
+    long n = 0, d = 0; int mt = 0;
+    if (fscanf(info, "%ld %ld %d", &n, &d, &mt) != 3 || n < 0 || d < 0) { fclose(info); printf("OSWALD: info file is malformed.\n"); return 2; }
+    fclose(info);
+    snprintf(filename, sizeof filename, "%s.seq", prefix);
+    int fd = open(filename, O_RDONLY);
+    if (fd < 0) { printf("OSWALD: An error occurred while opening sequence file.\n"); return 2; }
+    struct stat st;
+    fstat(fd, &st);
+    size_t need = (size_t)n * 2 + (size_t)d;
+    if ((size_t)st.st_size < need) { close(fd); printf("OSWALD: sequence file is shorter than the info file says.\n"); return 2; }
+    void *map = need ? mmap(NULL, need, PROT_READ, MAP_PRIVATE, fd, 0) : NULL;
+    close(fd);
+    if (need && map == MAP_FAILED) { printf("OSWALD: An error occurred while mapping sequence file.\n"); return 2; }
+    db->map = map; db->map_size = need;
+    db->n_seqs = (uint64_t)n; db->n_residues = (uint64_t)d; db->max_title_length = mt;
+    db->offsets = (uint64_t *)malloc(((size_t)n + 1) * sizeof(uint64_t));
+    if (!db->offsets) { printf("OSWALD: An error occurred while allocating memory.\n"); return 1; }
+    const uint16_t *lens = (const uint16_t *)map;
+    uint64_t acc = 0;
+    for (long i = 0; i < n; ++i) { db->offsets[i] = acc; acc += lens[i]; if (lens[i] > db->max_len) db->max_len = lens[i]; }
+    db->offsets[n] = acc;
+    if (acc != (uint64_t)d) { printf("OSWALD: sequence lengths do not add up to the residue count.\n"); return 2; }
+    db->residues = (uint8_t *)map + (size_t)n * 2;
+    return 0;
+}
+
+void free_database(osw_database *db) {
+    if (db->map) munmap(db->map, db->map_size);
+    free(db->offsets);
+    memset(db, 0, sizeof *db);
+}
+
+/* The reference loads all N titles (sequences.c:1096-1127); only the printed ones are needed:
+ * one sequential scan of X.desc picks the requested lines. */
+int load_database_headers(const char *prefix, const uint32_t *indices, size_t n, char **result) {
+    char filename[4096];
+    snprintf(filename, sizeof filename, "%s.desc", prefix);
+    FILE *f = fopen(filename, "r");
+    if (!f) { printf("OSWALD: An error occurred while opening sequence description file.\n"); return 3; }
+    /* order the requests by index */
+    size_t *order = (size_t *)malloc((n ? n : 1) * sizeof(size_t));
+    for (size_t i = 0; i < n; ++i) order[i] = i;
+    for (size_t i = 1; i < n; ++i) {          /* insertion sort: n is nq*top, small */
+        size_t v = order[i], j = i;
+        while (j && indices[order[j - 1]] > indices[v]) { order[j] = order[j - 1]; --j; }
+        order[j] = v;
+    }
+    for (size_t i = 0; i < n; ++i) result[i] = NULL;
+    char *line = NULL; size_t cap = 0; ssize_t len;
+    uint64_t lineno = 0; size_t k = 0;
+    while (k < n && (len = getline(&line, &cap, f)) >= 0) {
+        while (k < n && indices[order[k]] == lineno) {
+            result[order[k]] = strdup(line);
+            ++k;
+        }
+        ++lineno;
+    }
+    free(line); free(order);
+    fclose(f);
+    for (size_t i = 0; i < n; ++i) if (!result[i]) result[i] = strdup(">?\n");
+    return 0;
+}

@@ -150,3 +150,44 @@ def test_u16_dataflow_model_matches_oracle(G, R):
         got = emu_u16.score_chunk(seqs, list(q), G, R, mat, go, ge)
         want = np.array([O.sw_score(q, s, mat, go, ge) for s in seqs])
         assert np.array_equal(got, want)
+
+
+def _cli():
+    path = os.path.join(ROOT, "oswald_b200", "oswald")
+    if not os.path.exists(path):
+        pytest.skip("CLI not built")
+    return path
+
+
+def test_cli_preprocess_is_byte_compatible_with_the_reference(built, tmp_path):
+    """`-O preprocess` writes the reference's X.info/X.seq/X.desc: compared with the files the
+    reference binary itself writes (when it was compiled here) and with the host mirror."""
+    import gzip, shutil, subprocess
+    meta = load_case("g2_overflow")
+    fasta = tmp_path / "db.fasta"
+    with gzip.open(meta["db_fasta"], "rb") as g, open(fasta, "wb") as f:
+        shutil.copyfileobj(g, f)
+    subprocess.run([_cli(), "-O", "preprocess", "-i", str(fasta), "-o", str(tmp_path / "mine")], check=True)
+    db = ob.preprocess_db(meta["db_fasta"])
+    n, d, mt = open(tmp_path / "mine.info").read().split()
+    assert int(n) == db.n_seqs and int(d) == db.n_residues
+    raw = open(tmp_path / "mine.seq", "rb").read()
+    lens = np.frombuffer(raw[:2 * db.n_seqs], dtype="<u2")
+    assert np.array_equal(lens, np.diff(db.offsets.astype(np.int64)))
+    assert np.array_equal(np.frombuffer(raw[2 * db.n_seqs:], dtype=np.uint8), db.residues)
+    assert [l.rstrip("\n")[1:] for l in open(tmp_path / "mine.desc")] == meta["desc"]
+    ref = os.path.join(ROOT, "oracle", "_ref", "oswald_ref")
+    if os.path.exists(ref):
+        subprocess.run([ref, "-O", "preprocess", "-i", "db.fasta", "-o", "ref", "-c", "2"], cwd=tmp_path, check=True,
+                       capture_output=True)
+        for ext in ("info", "seq", "desc"):
+            assert open(tmp_path / ("mine." + ext), "rb").read() == open(tmp_path / ("ref." + ext), "rb").read(), ext
+
+
+def test_cli_rejects_bad_options(built):
+    import subprocess
+    cli = _cli()
+    assert subprocess.run([cli, "-O", "search", "-q", "x"], capture_output=True).returncode != 0      # -d missing
+    assert subprocess.run([cli, "-O", "search", "-q", "x", "-d", "y", "-s", "blosum99"], capture_output=True).returncode != 0
+    assert subprocess.run([cli, "-O", "search", "-q", "x", "-d", "y", "-g", "300"], capture_output=True).returncode != 0
+    assert subprocess.run([cli, "-O", "bogus"], capture_output=True).returncode != 0
