@@ -125,6 +125,10 @@ size_t osw_merge_hits(const osw_hit *const *lists, const uint32_t *counts, int n
  * [1] VIMNMX3.U16x2, [2] the 6-instruction cell-pair step as issued by the u16 kernel
  * (cell updates per SM-cycle), [3] IMAD, [4] SM clock in MHz during the run. */
 int osw_calibrate(int device, double out[8]);
+/* Co-issue probe: for 12 instruction classes (VIADDMNMX.U16x2, VIMNMX3.U16x2, VIADD, IMAD, HMNMX2,
+ * VIMNMX.U16x2, VIMNMX.U32, LOP3, FMNMX, PRMT, SHF, HADD2) out[3k..3k+2] = thread instructions per
+ * SM-cycle of the class alone, of 8 VIADDMNMX + 8 of it, of 8 VIADDMNMX + 4 of it.  n_out >= 36. */
+int osw_calibrate_mix(int device, double *out, int n_out);
 
 /* ---- substitution matrices: the reference's eight tables (submat.c:4-227), selected by the
  * -s name (arguments.c:94-111).  out[24*32], m[r*32+c].  0 on success, -1 unknown name. */

@@ -42,6 +42,7 @@ SYMBOLS = {
     "osw_set_kernels": (C.c_int, [C.c_void_p, C.c_int]),
     "osw_merge_hits": (C.c_size_t, [C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.c_int, C.c_uint32, C.c_void_p]),
     "osw_calibrate": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "osw_calibrate_mix": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_int]),
     "osw_matrix_count": (C.c_int, []),
     "osw_matrix_name": (C.c_char_p, [C.c_int]),
     "osw_matrix_by_name": (C.c_int, [C.c_char_p, C.c_void_p]),

@@ -132,3 +132,98 @@ extern "C" int osw_calibrate(int device, double out[8]) {
     cudaFree(g.cycles); cudaFree(g.sink);
     return rc ? OSW_E_CUDA : OSW_OK;
 }
+
+// ---- co-issue probe: which instruction classes issue alongside the DPX add-max ----------------
+// mix_kernel<A, B> runs 8 independent chains of op A and 8 of op B, interleaved.  If the total
+// rate of <A,B> is about twice A's own rate the two classes use different issue pipes.
+namespace {
+
+enum { OP_NONE = -1, OP_VIADDMNMX = 0, OP_VIMNMX3, OP_VIADD, OP_IMAD, OP_HMNMX2, OP_VIMNMX2, OP_IMNMX, OP_LOP3,
+       OP_FMNMX, OP_PRMT, OP_SHF, OP_HADD2, OP_COUNT };
+
+template <int OP>
+__device__ __forceinline__ uint32_t apply(uint32_t x, uint32_t a, uint32_t b) {
+    uint32_t r = x;
+    if (OP == OP_VIADDMNMX) r = __viaddmax_u16x2(x, a, b);
+    else if (OP == OP_VIMNMX3) r = __vimax3_u16x2(x, a, b);
+    else if (OP == OP_VIADD) asm volatile("add.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(a));
+    else if (OP == OP_IMAD) asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(a), "r"(b));
+    else if (OP == OP_HMNMX2) asm volatile("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(a));
+    else if (OP == OP_VIMNMX2) r = __vmaxu2(x, a);
+    else if (OP == OP_IMNMX) asm volatile("max.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(a));
+    else if (OP == OP_LOP3) asm volatile("xor.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(a));
+    else if (OP == OP_FMNMX) asm volatile("max.f32 %0, %1, %2;" : "=f"(*(float *)&r) : "f"(__uint_as_float(x)), "f"(__uint_as_float(a)));
+    else if (OP == OP_PRMT) asm volatile("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(r) : "r"(x), "r"(a));
+    else if (OP == OP_SHF) asm volatile("shf.l.wrap.b32 %0, %1, %2, 3;" : "=r"(r) : "r"(x), "r"(a));
+    else if (OP == OP_HADD2) asm volatile("add.f16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(a));
+    return r;
+}
+
+template <int A, int B, int NB>
+__global__ void __launch_bounds__(CAL_THREADS) mix_kernel(CalArgs g) {
+    uint32_t x[8], y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { x[k] = g.a * (threadIdx.x + k + 1); y[k] = g.b + threadIdx.x * (k + 3); }
+    long long t0 = clock64();
+    for (int it = 0; it < CAL_ITERS; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x[k] = apply<A>(x[k], g.a, g.b);
+            if (B != OP_NONE && k < NB) y[k] = apply<B>(y[k], g.b, g.a);
+        }
+    }
+    long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc ^= x[k] ^ y[k];
+    g.sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) atomicMax(g.cycles, (unsigned long long)(t1 - t0));
+}
+
+template <int A, int B, int NB>
+double run_mix(int n_sms, CalArgs g) {
+    cudaMemset(g.cycles, 0, sizeof(unsigned long long));
+    mix_kernel<A, B, NB><<<n_sms, CAL_THREADS>>>(g);
+    cudaMemset(g.cycles, 0, sizeof(unsigned long long));
+    mix_kernel<A, B, NB><<<n_sms, CAL_THREADS>>>(g);
+    unsigned long long c = 1;
+    cudaMemcpy(&c, g.cycles, sizeof c, cudaMemcpyDeviceToHost);
+    const double n_instr = (double)(CAL_THREADS / 32) * CAL_ITERS * (8 + (B == OP_NONE ? 0 : NB)) * 32;
+    return n_instr / (double)c;          // thread instructions per SM-cycle, both classes together
+}
+
+template <int B>
+void probe_pair(int n_sms, CalArgs g, double *alone, double *with_dpx, double *with_dpx_half) {
+    *alone = run_mix<B, OP_NONE, 0>(n_sms, g);
+    *with_dpx = run_mix<OP_VIADDMNMX, B, 8>(n_sms, g);
+    *with_dpx_half = run_mix<OP_VIADDMNMX, B, 4>(n_sms, g);
+}
+
+}  // namespace
+
+// out[3*k + {0,1,2}] for k = op class: rate alone, total rate of 8 DPX + 8 of it, 8 DPX + 4 of it.
+extern "C" int osw_calibrate_mix(int device, double *out, int n_out) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return OSW_E_NODEV;
+    if (cudaSetDevice(device) != cudaSuccess) return OSW_E_CUDA;
+    if (n_out < 3 * OP_COUNT) return OSW_E_ARG;
+    const int n_sms = prop.multiProcessorCount;
+    CalArgs g;
+    g.a = 0x00030005u; g.b = 0x00110013u; g.one = 1u; g.ngoe = 0x000c000cu; g.nge = 0xfffefffeu; g.B = 0x00400040u;
+    if (cudaMalloc(&g.cycles, 2 * sizeof(unsigned long long)) != cudaSuccess) return OSW_E_NOMEM;
+    if (cudaMalloc(&g.sink, (size_t)n_sms * CAL_THREADS * sizeof(uint32_t)) != cudaSuccess) return OSW_E_NOMEM;
+    probe_pair<OP_VIADDMNMX>(n_sms, g, out + 0, out + 1, out + 2);
+    probe_pair<OP_VIMNMX3>(n_sms, g, out + 3, out + 4, out + 5);
+    probe_pair<OP_VIADD>(n_sms, g, out + 6, out + 7, out + 8);
+    probe_pair<OP_IMAD>(n_sms, g, out + 9, out + 10, out + 11);
+    probe_pair<OP_HMNMX2>(n_sms, g, out + 12, out + 13, out + 14);
+    probe_pair<OP_VIMNMX2>(n_sms, g, out + 15, out + 16, out + 17);
+    probe_pair<OP_IMNMX>(n_sms, g, out + 18, out + 19, out + 20);
+    probe_pair<OP_LOP3>(n_sms, g, out + 21, out + 22, out + 23);
+    probe_pair<OP_FMNMX>(n_sms, g, out + 24, out + 25, out + 26);
+    probe_pair<OP_PRMT>(n_sms, g, out + 27, out + 28, out + 29);
+    probe_pair<OP_SHF>(n_sms, g, out + 30, out + 31, out + 32);
+    probe_pair<OP_HADD2>(n_sms, g, out + 33, out + 34, out + 35);
+    cudaFree(g.cycles); cudaFree(g.sink);
+    return cudaDeviceSynchronize() == cudaSuccess ? OSW_OK : OSW_E_CUDA;
+}

@@ -225,3 +225,15 @@ def calibrate(device=0):
     return {"viaddmnmx_u16x2_per_sm_clk": out[0], "vimnmx3_u16x2_per_sm_clk": out[1],
             "cells_per_sm_clk_step_imad": out[2], "imad_per_sm_clk": out[3], "sm_mhz": out[4],
             "cells_per_sm_clk_step_plain_sub": out[5], "cells_per_sm_clk_step_with_lds": out[6]}
+
+
+MIX_CLASSES = ["VIADDMNMX.U16x2", "VIMNMX3.U16x2", "VIADD", "IMAD", "HMNMX2", "VIMNMX.U16x2", "VIMNMX.U32", "LOP3",
+               "FMNMX", "PRMT", "SHF", "HADD2"]
+
+
+def calibrate_mix(device=0):
+    """Issue rates (thread instructions per SM-cycle): alone / with 8 DPX + 8 / with 8 DPX + 4."""
+    out = (C.c_double * 36)()
+    capi.check(capi.lib().osw_calibrate_mix(device, out, 36), "osw_calibrate_mix")
+    return {name: {"alone": out[3 * k], "dpx8_plus8_total": out[3 * k + 1], "dpx8_plus4_total": out[3 * k + 2]}
+            for k, name in enumerate(MIX_CLASSES)}
