@@ -130,7 +130,7 @@ sw_u16_kernel(const KArgs a) {
     const uint32_t mail_self = (uint32_t)__cvta_generic_to_shared(s_mail + wib * 32 + lane);
     const uint32_t mail_up = mail_self - 16;     // lane-1's mailbox (unused when t == 0)
     const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(s_ring + (wib * GROUPS + grp) * RING);
-    const uint32_t B2 = a.bias2, NGE = a.nge2, NGOE = a.ngoe_word, ONE = a.one;
+    const uint32_t B2 = a.bias2, NGE = a.nge2, GOE2 = 0u - a.ngoe_word;
     const bool multi_in = p.bound_in != nullptr;
 
     for (;;) {
@@ -200,23 +200,29 @@ sw_u16_kernel(const KArgs a) {
                     diag_top = B2;
                 }
                 const uint32_t paddr = prof_lane + (lf & OSW_COL_CODE) * PITCH_B;
-                uint32_t F = in.y, diag = diag_top, cm = in.z, Heven = B2;
+                // Row sweep.  t (the diagonal term) of row r+1 is issued before H of row r is
+                // written, so that H can overwrite Hl[r] in place (no register rotation).
+                uint32_t F = in.y, cm = in.z, Heven = B2;
+                uint4 sv = lds128_const(paddr);
+                uint32_t t_next = __viaddmax_u16x2(diag_top, sv.x, E[0]);
 #pragma unroll
                 for (int k = 0; k < R / 4; ++k) {
-                    const uint4 sv = lds128_const(paddr + k * 16);
-                    const uint32_t sc[4] = {sv.x, sv.y, sv.z, sv.w};
+                    uint4 sn = sv;
+                    if (k + 1 < R / 4) sn = lds128_const(paddr + (k + 1) * 16);
+                    const uint32_t s_after[4] = {sv.y, sv.z, sv.w, sn.x};    // score of the row after rr
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
                         const int r = 4 * k + rr;
-                        const uint32_t tt = __viaddmax_u16x2(diag, sc[rr], E[r]);
+                        const uint32_t tt = t_next;
+                        if (r + 1 < R) t_next = __viaddmax_u16x2(Hl[r], s_after[rr], E[r + 1]);
                         const uint32_t H = __vimax3_u16x2(tt, F, B2);
-                        const uint32_t u = imad_add(H, ONE, NGOE);
+                        const uint32_t u = H - GOE2;
                         E[r] = __viaddmax_u16x2(E[r], NGE, u);
                         F = __viaddmax_u16x2(F, NGE, u);
-                        diag = Hl[r];
                         Hl[r] = H;
                         if (rr & 1) cm = __vimax3_u16x2(cm, Heven, H); else Heven = H;
                     }
+                    sv = sn;
                 }
                 diag_top = in.x;
                 run = __vmaxu2(run, cm);
