@@ -511,6 +511,17 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
         tm.rescore_ms = std::max(tm.rescore_ms, (double)ms_resc);
         tm.topr_ms = std::max(tm.topr_ms, (double)ms_top);
         if (i == 0) for (uint32_t k = 0; k < slots[i]; ++k) tm.sm_cycles += d.h_cycles[k];
+        if (i == 0 && getenv("OSW_TRACE")) {
+            // per-launch report: geometry, elapsed SM cycles, padded cell updates per SM-cycle
+            uint32_t k = 0;
+            for (const QueryPair &qp : pairs)
+                for (int pass = 0; pass < qp.cfg.passes && k < slots[i]; ++pass, ++k) {
+                    const double cells = 2.0 * qp.cfg.G * qp.cfg.R * (double)d.shard.n_residues;
+                    fprintf(stderr, "osw trace: pair (%u,%u) G=%d R=%d pass %d/%d  %llu cycles  %.2f padded cells/SM-clk\n",
+                            qp.len_a, qp.len_b, qp.cfg.G, qp.cfg.R, pass + 1, qp.cfg.passes,
+                            (unsigned long long)d.h_cycles[k], cells / ((double)d.h_cycles[k] * d.n_sms));
+                }
+        }
         const uint32_t r = (uint32_t)std::min<uint64_t>((uint64_t)top_r, N);
         per_dev[i].resize((size_t)nq * r);
         for (int q = 0; q < nq; ++q) {

@@ -45,6 +45,10 @@ __host__ __device__ constexpr int prof_quads(int G, int R) { return (G * pitch_q
 __host__ __device__ constexpr int prof_copies(int G) { return G == 4 ? 2 : 1; }
 __host__ __device__ constexpr size_t prof_copy_bytes(int G, int R) { return (size_t)24 * prof_quads(G, R) * 16; }
 __host__ __device__ constexpr int block_threads(int R) { return R > 36 ? 384 : 512; }
+// A lane's R rows are swept as NUM_CHAINS independent segments (segment c works one column
+// behind segment c-1): two dependency chains per thread keep the DPX pipe fed.
+constexpr int NUM_CHAINS = 2;
+__host__ __device__ constexpr int seg_begin(int R, int NC, int c) { return ((R / 4) * c + NC - 1) / NC; }   // first quad of segment c
 
 __device__ __forceinline__ uint32_t imad_add(uint32_t h, uint32_t one, uint32_t c) {
     uint32_t u;
@@ -86,6 +90,7 @@ sw_u16_kernel(const KArgs a) {
     constexpr int PITCH_B = prof_quads(G, R) * 16;
     constexpr int COPY_B = (int)prof_copy_bytes(G, R);
     constexpr int EPL = 32 / G;                 // ring entries each lane fills per 32-column block
+    constexpr int NC = NUM_CHAINS;              // independent row segments per lane
 
     extern __shared__ __align__(128) unsigned char smem[];
     // layout: [profile copies][mailbox: WARPS*32 uint4][rings: WARPS*GROUPS*RING uint4]
@@ -144,7 +149,7 @@ sw_u16_kernel(const KArgs a) {
         const bool have = ci < p.n_chunks;
         osw_chunk ck;
         if (have) ck = p.chunks[ci]; else { ck.stream_off = 0; ck.n_cols = 0; ck.n_seqs = 0; ck.seq0 = 0; ck.canon0 = 0; }
-        uint32_t steps = have ? ck.n_cols + G - 1 : 0;
+        uint32_t steps = have ? ck.n_cols + NC * G - 1 : 0;
 #pragma unroll
         for (int o = 16; o; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
         const uint32_t n_blocks = (steps + 31) / 32;
@@ -181,7 +186,10 @@ sw_u16_kernel(const KArgs a) {
         uint32_t Hl[R], E[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) { Hl[r] = B2; E[r] = B2; }
-        uint32_t diag_top = B2, run = B2;
+        uint32_t diag[NC], run = B2;
+        uint4 mid[NC];                   // mid[c]: message segment c-1 produced in the previous step
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { diag[c] = B2; mid[c] = make_uint4(B2, B2, B2, OSW_COL_PADBYTE); }
         uint32_t seq = ck.seq0;
         sts128(mail_self, make_uint4(B2, B2, B2, OSW_COL_PADBYTE));
         __syncwarp();
@@ -192,45 +200,74 @@ sw_u16_kernel(const KArgs a) {
             for (uint32_t i = 0; i < 32; ++i) {
                 const uint32_t step = blk * 32 + i;
                 const uint32_t in_addr = t == 0 ? ring_base + (step & (RING - 1)) * 16 : mail_up;
-                const uint4 in = lds128(in_addr);
-                const uint32_t lf = in.w;
-                if (lf & OSW_COL_FIRST) {
+                uint4 msg[NC];
+                msg[0] = lds128(in_addr);
 #pragma unroll
-                    for (int r = 0; r < R; ++r) { Hl[r] = B2; E[r] = B2; }
-                    diag_top = B2;
+                for (int c = 1; c < NC; ++c) msg[c] = mid[c];
+                uint32_t paddr[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    if (msg[c].w & OSW_COL_FIRST) {
+#pragma unroll
+                        for (int r = 4 * seg_begin(R, NC, c); r < 4 * seg_begin(R, NC, c + 1); ++r) { Hl[r] = B2; E[r] = B2; }
+                        diag[c] = B2;
+                    }
+                    paddr[c] = prof_lane + (msg[c].w & OSW_COL_CODE) * PITCH_B + seg_begin(R, NC, c) * 16;
                 }
-                const uint32_t paddr = prof_lane + (lf & OSW_COL_CODE) * PITCH_B;
-                // Row sweep.  t (the diagonal term) of row r+1 is issued before H of row r is
-                // written, so that H can overwrite Hl[r] in place (no register rotation).
-                uint32_t F = in.y, cm = in.z, Heven = B2;
-                uint4 sv = lds128_const(paddr);
-                uint32_t t_next = __viaddmax_u16x2(diag_top, sv.x, E[0]);
+                // Row sweeps of the NC segments, interleaved: they are independent dependency
+                // chains.  t (the diagonal term) of row r+1 is issued before H of row r is written,
+                // so that H can overwrite Hl[r] in place.
+                uint32_t F[NC], cm[NC], Heven[NC], t_next[NC];
+                uint4 sv[NC];
 #pragma unroll
-                for (int k = 0; k < R / 4; ++k) {
-                    uint4 sn = sv;
-                    if (k + 1 < R / 4) sn = lds128_const(paddr + (k + 1) * 16);
-                    const uint32_t s_after[4] = {sv.y, sv.z, sv.w, sn.x};    // score of the row after rr
+                for (int c = 0; c < NC; ++c) {
+                    F[c] = msg[c].y; cm[c] = msg[c].z; Heven[c] = B2;
+                    sv[c] = lds128_const(paddr[c]);
+                    t_next[c] = __viaddmax_u16x2(diag[c], sv[c].x, E[4 * seg_begin(R, NC, c)]);
+                }
+#pragma unroll
+                for (int kk = 0; kk < seg_begin(R, NC, 1); ++kk) {
+                    uint4 sn[NC];
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        sn[c] = sv[c];
+                        if (kk + 1 < seg_begin(R, NC, c + 1) - seg_begin(R, NC, c)) sn[c] = lds128_const(paddr[c] + (kk + 1) * 16);
+                    }
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
-                        const int r = 4 * k + rr;
-                        const uint32_t tt = t_next;
-                        if (r + 1 < R) t_next = __viaddmax_u16x2(Hl[r], s_after[rr], E[r + 1]);
-                        const uint32_t H = __vimax3_u16x2(tt, F, B2);
-                        const uint32_t u = H - GOE2;
-                        E[r] = __viaddmax_u16x2(E[r], NGE, u);
-                        F = __viaddmax_u16x2(F, NGE, u);
-                        Hl[r] = H;
-                        if (rr & 1) cm = __vimax3_u16x2(cm, Heven, H); else Heven = H;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            if (kk < seg_begin(R, NC, c + 1) - seg_begin(R, NC, c)) {
+                                const int r = 4 * (seg_begin(R, NC, c) + kk) + rr;
+                                const uint32_t s_after = rr == 0 ? sv[c].y : rr == 1 ? sv[c].z : rr == 2 ? sv[c].w : sn[c].x;
+                                const uint32_t tt = t_next[c];
+                                if (r + 1 < 4 * seg_begin(R, NC, c + 1)) t_next[c] = __viaddmax_u16x2(Hl[r], s_after, E[r + 1]);
+                                const uint32_t H = __vimax3_u16x2(tt, F[c], B2);
+                                const uint32_t u = H - GOE2;
+                                E[r] = __viaddmax_u16x2(E[r], NGE, u);
+                                F[c] = __viaddmax_u16x2(F[c], NGE, u);
+                                Hl[r] = H;
+                                if (rr & 1) cm[c] = __vimax3_u16x2(cm[c], Heven[c], H); else Heven[c] = H;
+                            }
+                        }
                     }
-                    sv = sn;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) sv[c] = sn[c];
                 }
-                diag_top = in.x;
-                run = __vmaxu2(run, cm);
+                // hand the segments' bottom rows on: segment c -> segment c+1 (next step), last -> next lane
+#pragma unroll
+                for (int c = 0; c < NC; ++c) diag[c] = msg[c].x;
+#pragma unroll
+                for (int c = NC - 1; c >= 1; --c)
+                    mid[c] = make_uint4(Hl[4 * seg_begin(R, NC, c) - 1], F[c - 1], cm[c - 1], msg[c - 1].w);
+                const uint32_t lf = msg[NC - 1].w;
+                const uint32_t Hbot = Hl[R - 1], Fbot = F[NC - 1], cmbot = cm[NC - 1];
+                run = __vmaxu2(run, cmbot);
                 if (t == G - 1) {
-                    // column index of this lane in the chunk: step - t
-                    const uint32_t col = step - (G - 1);
+                    // column this lane's last segment just finished
+                    const uint32_t col = step - (NC * G - 1);
                     if (p.bound_out && col < cols_padded)
-                        __stcg(p.bound_out + ck.stream_off + col, make_uint2(Hl[R - 1], F));
+                        __stcg(p.bound_out + ck.stream_off + col, make_uint2(Hbot, Fbot));
                     if (lf & OSW_COL_LAST) {
                         const uint32_t lo = run & 0xffffu, hi = run >> 16;
                         const int sa = lo >= FLAG_THRESHOLD ? OSW_SCORE_FLAGGED : (int)(lo - a.bias);
@@ -242,7 +279,7 @@ sw_u16_kernel(const KArgs a) {
                     }
                 }
                 __syncwarp();
-                sts128(mail_self, make_uint4(Hl[R - 1], F, cm, lf));
+                sts128(mail_self, make_uint4(Hbot, Fbot, cmbot, lf));
                 __syncwarp();
             }
             commit(blk + 1);

@@ -26,14 +26,33 @@ def build_stream(seqs):
     return out
 
 
-def run_pass(stream, n_seqs, query, row0, G, R, mat, go, ge, bound_in, want_out, scores):
-    """One launch: rows row0 .. row0+G*R-1 of `query` against the chunk `stream`."""
+def segment_rows(R, chains):
+    """Row counts of the segments a lane's R rows are split into (seg_begin() in sw_u16.cu)."""
+    q = R // 4
+    begin = [(q * c + chains - 1) // chains for c in range(chains + 1)]
+    return [4 * (begin[c + 1] - begin[c]) for c in range(chains)]
+
+
+def run_pass(stream, n_seqs, query, row0, G, R, mat, go, ge, bound_in, want_out, scores, chains=1):
+    """One launch: rows row0 .. row0+G*R-1 of `query` against the chunk `stream`.  With
+    chains > 1 every lane is `chains` consecutive stations of the systolic array (its row
+    segments), each one column behind the previous one."""
     goe = go + ge
     B = goe + ge + 32
     nge = (0x10000 - ge) & M16
-    rows = [[(int(query[row0 + t * R + r]) if row0 + t * R + r < len(query) else PAD) for r in range(R)] for t in range(G)]
-    Hl = [[B] * R for _ in range(G)]
-    E = [[B] * R for _ in range(G)]
+    if chains > 1:
+        seg = segment_rows(R, chains)
+        stations, first = [], row0
+        for t in range(G):
+            for n_rows in seg:
+                stations.append([(int(query[first + r]) if first + r < len(query) else PAD) for r in range(n_rows)])
+                first += n_rows
+        rows = stations
+        G = len(rows)
+    else:
+        rows = [[(int(query[row0 + t * R + r]) if row0 + t * R + r < len(query) else PAD) for r in range(R)] for t in range(G)]
+    Hl = [[B] * len(rows[t]) for t in range(G)]
+    E = [[B] * len(rows[t]) for t in range(G)]
     diag_top = [B] * G
     run = B
     seq = 0
@@ -53,12 +72,12 @@ def run_pass(stream, n_seqs, query, row0, G, R, mat, go, ge, bound_in, want_out,
                 msg = mail[t - 1]
             hup, fup, cm, lf = msg
             if lf & FIRST:
-                Hl[t] = [B] * R
-                E[t] = [B] * R
+                Hl[t] = [B] * len(rows[t])
+                E[t] = [B] * len(rows[t])
                 diag_top[t] = B
             code = lf & 31
             F, diag = fup, diag_top[t]
-            for r in range(R):
+            for r in range(len(rows[t])):
                 sc = int(mat[rows[t][r] * 32 + code]) & M16
                 tt = max((diag + sc) & M16, E[t][r])
                 H = max(tt, F, B)
@@ -73,19 +92,19 @@ def run_pass(stream, n_seqs, query, row0, G, R, mat, go, ge, bound_in, want_out,
                 run = max(run, cm)
                 col = step - (G - 1)
                 if want_out and 0 <= col < n:
-                    bound_out[col] = (Hl[t][R - 1], F)
+                    bound_out[col] = (Hl[t][-1], F)
                 if lf & LAST:
                     val = FLAGGED if run >= THRESH else run - B
                     scores[seq] = max(scores[seq], val)
                     seq += 1
                     run = B
-            new_mail[t] = (Hl[t][R - 1], F, cm, lf)
+            new_mail[t] = (Hl[t][-1], F, cm, lf)
         mail = new_mail
     assert seq == n_seqs
     return bound_out
 
 
-def score_chunk(seqs, query, G, R, mat, go, ge):
+def score_chunk(seqs, query, G, R, mat, go, ge, chains=1):
     """Scores of `query` against every sequence of one chunk (FLAGGED where the kernel would flag)."""
     stream = build_stream(seqs)
     n_seqs = sum(1 for s in seqs if len(s))
@@ -93,5 +112,5 @@ def score_chunk(seqs, query, G, R, mat, go, ge):
     passes = max(1, -(-len(query) // (G * R)))
     bound = None
     for p in range(passes):
-        bound = run_pass(stream, n_seqs, query, p * G * R, G, R, mat, go, ge, bound, p + 1 < passes, scores)
+        bound = run_pass(stream, n_seqs, query, p * G * R, G, R, mat, go, ge, bound, p + 1 < passes, scores, chains)
     return np.array(scores, dtype=np.int64)

@@ -135,8 +135,8 @@ def test_merge_hits_reference_order(built):
     assert merge_hits([[], [(3, 1)]], 5) == [(3, 1)]
 
 
-@pytest.mark.parametrize("G,R", [(1, 4), (2, 8), (4, 4), (4, 12)])
-def test_u16_dataflow_model_matches_oracle(G, R):
+@pytest.mark.parametrize("G,R,chains", [(1, 4, 1), (2, 8, 1), (4, 4, 1), (4, 12, 1), (2, 12, 2), (4, 8, 2), (1, 20, 2)])
+def test_u16_dataflow_model_matches_oracle(G, R, chains):
     """The systolic/biased-unsigned scheme of sw_u16.cu, modelled step by step in Python."""
     rng = np.random.default_rng(100 + G * R)
     for trial in range(12):
@@ -147,7 +147,7 @@ def test_u16_dataflow_model_matches_oracle(G, R):
         q = AA[rng.integers(0, 20, size=int(rng.integers(1, 3 * G * R)))]
         if trial % 3 == 0:
             seqs[0] = np.concatenate([q[:len(q) // 2 + 1], seqs[0]])
-        got = emu_u16.score_chunk(seqs, list(q), G, R, mat, go, ge)
+        got = emu_u16.score_chunk(seqs, list(q), G, R, mat, go, ge, chains)
         want = np.array([O.sw_score(q, s, mat, go, ge) for s in seqs])
         assert np.array_equal(got, want)
 
