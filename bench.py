@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=20000, help="sequences in the CPU baseline's sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels", type=int, default=3, help="kernel mask (1|2 = default, 2 = 32-bit only)")
+    ap.add_argument("--chunk-cols", type=int, default=0, help="residues per chunk (0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -234,7 +235,7 @@ def main():
 
     s = ob.Searcher(devices=[local_rank])
     s.set_kernels(args.kernels)
-    s.load_db(db, shard_rank=rank, shard_count=world)
+    s.load_db(db, shard_rank=rank, shard_count=world, max_chunk_residues=args.chunk_cols)
     st = s.stats()
 
     def barrier():
@@ -294,23 +295,31 @@ def main():
         # roofline of the dominant kernel (sw_u16_kernel): cell updates per SM-cycle against the
         # calibrated DPX issue rate; 3 packed instructions per cell.
         score_ms = float(np.mean([x["score_ms"] for x in tms]))
-        sm_cycles = float(np.mean([x["sm_cycles"] for x in tms]))
+        sm_cycles = float(np.mean([x["sm_cycles"] for x in tms]))       # busy SM-cycles summed over SMs
         local_cells = tm["cells"]
         r_dpx = cal["viaddmnmx_u16x2_per_sm_clk"]
         peak_cells_clk = 2.0 * r_dpx / 6.0
-        ach_cells_clk = local_cells / (sm_cycles * n_sms) if sm_cycles else None
-        eff_mhz = sm_cycles / (score_ms * 1e3) if score_ms else None
+        sm_mhz = clocks["sm_mhz"] or cal["sm_mhz"]
+        peak_gcups = peak_cells_clk * n_sms * sm_mhz * 1e6 / 1e9
+        achieved_gcups = (local_cells / (score_ms / 1e3) / 1e9) if score_ms else None
+        busy_cells_clk = local_cells / sm_cycles if sm_cycles else None
         roofline = {"bound": "alu", "kernel": "sw_u16_kernel (packed 16-bit DPX)",
-                    "achieved": (local_cells / (score_ms / 1e3) / 1e9) if score_ms else None,
-                    "peak": peak_cells_clk * n_sms * (eff_mhz or 0) * 1e6 / 1e9, "unit": "GCUPS",
-                    "frac": (ach_cells_clk / peak_cells_clk) if ach_cells_clk else None,
-                    "achieved_cells_per_sm_clk": ach_cells_clk, "peak_cells_per_sm_clk": peak_cells_clk,
-                    "r_dpx_thread_instr_per_sm_clk": r_dpx, "sm_mhz_during_kernel": eff_mhz,
-                    "padded_over_useful_cells": tm["padded_cells"] / max(local_cells, 1),
-                    "calibration": cal, "peak_source": "calibrated on this GPU in this run (osw_calibrate); 3 DPX instr/cell",
+                    "achieved": achieved_gcups, "peak": peak_gcups, "unit": "GCUPS",
+                    "frac": (achieved_gcups / peak_gcups) if achieved_gcups else None,
+                    "definition": "peak = 148 SMs x SM clock x (2 x R_dpx / 6) cell updates per SM-cycle: 3 packed DPX "
+                                  "instructions per cell (SURVEY.md 8(d)), R_dpx = measured VIADDMNMX.U16x2 issue rate; "
+                                  "achieved = useful (unpadded) cells / CUDA-event time of the first-stage launches",
+                    "peak_cells_per_sm_clk": peak_cells_clk, "r_dpx_thread_instr_per_sm_clk": r_dpx,
+                    "achieved_cells_per_busy_sm_clk": busy_cells_clk,
+                    "sm_busy_fraction": sm_cycles / (n_sms * sm_mhz * 1e3 * score_ms) if score_ms else None,
+                    "kernel_issue_bound_cells_per_sm_clk": 2.0 * r_dpx / 4.5,
+                    "frac_of_kernel_issue_bound": (achieved_gcups / (2.0 * r_dpx / 4.5 * n_sms * sm_mhz * 1e-3)) if achieved_gcups else None,
+                    "sm_mhz": sm_mhz, "padded_over_useful_cells": tm["padded_cells"] / max(local_cells, 1),
+                    "calibration": cal, "peak_source": "calibrated on this GPU in this run (osw_calibrate)",
                     "hbm": {"achieved_GBps": tm["db_stream_bytes"] / (score_ms / 1e3) / 1e9 if score_ms else None,
                             "peak_GBps": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-                            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0},
+                            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
+                            "algorithmic_bytes_per_cell": tm["db_stream_bytes"] / max(local_cells, 1)},
                     "traffic": None}
         out = {"metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -67,7 +67,7 @@ typedef struct osw_timing {
     uint64_t padded_cells;     /* cell updates actually issued by the first-stage kernels */
     uint64_t rescored_pairs;   /* (query, sequence) pairs that went to the 32-bit kernel */
     uint64_t launches;         /* kernels launched by this call (all GPUs) */
-    uint64_t sm_cycles;        /* elapsed SM cycles of the first-stage kernels (clock64, GPU 0) */
+    uint64_t sm_cycles;        /* busy SM-cycles of the first-stage kernels summed over the SMs of GPU 0 (clock64) */
     uint64_t db_stream_bytes;  /* database bytes read by the first-stage kernels (algorithmic) */
 } osw_timing;
 
@@ -123,8 +123,9 @@ size_t osw_merge_hits(const osw_hit *const *lists, const uint32_t *counts, int n
  * section 8(d)).  Runs dependent-chain-free micro-kernels on `device` and reports warp
  * instructions per SM-cycle * 32 = thread instructions per SM-cycle for: [0] VIADDMNMX.U16x2,
  * [1] VIMNMX3.U16x2, [2] the 6-instruction cell-pair step as issued by the u16 kernel
- * (cell updates per SM-cycle), [3] IMAD, [4] SM clock in MHz during the run. */
-int osw_calibrate(int device, double out[8]);
+ * (cell updates per SM-cycle), [3] IMAD, [4] SM clock in MHz during the run, [5..9] variants of
+ * the cell-pair step (see calib.cu). */
+int osw_calibrate(int device, double out[12]);
 /* Co-issue probe: for 12 instruction classes (VIADDMNMX.U16x2, VIMNMX3.U16x2, VIADD, IMAD, HMNMX2,
  * VIMNMX.U16x2, VIMNMX.U32, LOP3, FMNMX, PRMT, SHF, HADD2) out[3k..3k+2] = thread instructions per
  * SM-cycle of the class alone, of 8 VIADDMNMX + 8 of it, of 8 VIADDMNMX + 4 of it.  n_out >= 36. */

@@ -29,8 +29,9 @@ constexpr uint32_t FLAG_CAPACITY_MIN = 1u << 16;
 
 struct DevState {
     int dev = -1, n_sms = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr;      // st2: second lane for first-stage launches (tail overlap)
     cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // database shard
     osw_shard shard = {};
     uint8_t *h_stream = nullptr;               // pinned copy of shard.stream (source of re-uploads)
@@ -181,6 +182,11 @@ extern "C" int osw_init(int n_devices, const int *devices, osw_ctx **out) {
             osw_free(c); return cuda_fail(e, "stream setup", __LINE__);
         }
         for (auto &ev : d.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) { osw_free(c); return cuda_fail(e, "cudaEventCreate", __LINE__); }
+        if ((e = cudaStreamCreateWithFlags(&d.st2, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming)) != cudaSuccess) {
+            osw_free(c); return cuda_fail(e, "stream setup", __LINE__);
+        }
         if ((e = cudaMalloc(&d.d_matrix, 24 * 32)) != cudaSuccess ||
             (e = cudaMalloc(&d.d_counters, (1 + MAX_LAUNCH_SLOTS) * sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_task_counter, 2 * sizeof(unsigned long long))) != cudaSuccess ||
@@ -210,6 +216,9 @@ extern "C" void osw_free(osw_ctx *c) {
         if (d.h_cycles) cudaFreeHost(d.h_cycles);
         if (d.h_counts) cudaFreeHost(d.h_counts);
         for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
+        if (d.ev_fork) cudaEventDestroy(d.ev_fork);
+        if (d.ev_join) cudaEventDestroy(d.ev_join);
+        if (d.st2) cudaStreamDestroy(d.st2);
         if (d.st) cudaStreamDestroy(d.st);
     }
     delete[] c->devs;
@@ -390,7 +399,16 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
 
     uint32_t slot = 0;
     if (use_u16 && N) {
+        // Query pairs alternate between two streams: a launch is one persistent CTA per SM, so the
+        // next pair's CTAs move onto SMs as the previous launch's tail frees them.  Each stream has
+        // its own bottom-row buffer, updated in place (a warp writes a chunk's columns behind the
+        // ones it still has to read).
+        CK(cudaEventRecord(d.ev_fork, d.st));
+        CK(cudaStreamWaitEvent(d.st2, d.ev_fork, 0));
+        int pair_no = 0;
         for (const QueryPair &qp : pairs) {
+            const int lane_no = pair_no++ & 1;
+            cudaStream_t lane_st = lane_no ? d.st2 : d.st;
             const uint32_t rows_per_pass = (uint32_t)(qp.cfg.G * qp.cfg.R);
             for (int pass = 0; pass < qp.cfg.passes; ++pass) {
                 if (slot >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
@@ -401,13 +419,13 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
                 up.matrix = d.d_matrix;
                 up.scores_a = d.d_scores + (size_t)qp.a * N;
                 up.scores_b = qp.b >= 0 ? d.d_scores + (size_t)qp.b * N : nullptr;
-                up.bound_in = pass > 0 ? d.d_bound[(pass - 1) & 1] : nullptr;
-                up.bound_out = pass + 1 < qp.cfg.passes ? d.d_bound[pass & 1] : nullptr;
+                up.bound_in = pass > 0 ? d.d_bound[lane_no] : nullptr;
+                up.bound_out = pass + 1 < qp.cfg.passes ? d.d_bound[lane_no] : nullptr;
                 up.row0 = (uint32_t)pass * rows_per_pass;
                 up.gap_open_extend = go + ge; up.gap_extend = ge;
                 up.chunk_counter = d.d_counters + 1 + slot;
                 up.cycle_acc = d.d_cycles + slot;
-                if ((rc = osw_launch_u16(up, qp.cfg, d.n_sms, d.st)) != OSW_OK) {
+                if ((rc = osw_launch_u16(up, qp.cfg, d.n_sms, lane_st)) != OSW_OK) {
                     cuda_fail(cudaGetLastError(), "sw_u16 launch", __LINE__);
                     return rc;
                 }
@@ -415,6 +433,8 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
                 *padded_cells += (uint64_t)rows_per_pass * 2 * s.n_residues;
             }
         }
+        CK(cudaEventRecord(d.ev_join, d.st2));
+        CK(cudaStreamWaitEvent(d.st, d.ev_join, 0));
         CK(cudaEventRecord(d.ev[1], d.st));
         *launches += osw_collect_flagged(d.d_scores, N, nq, d.d_pairs, d.d_counters, flag_cap, d.st);
         CK(cudaMemcpyAsync(d.h_counts, d.d_counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, d.st));
@@ -517,9 +537,9 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
             for (const QueryPair &qp : pairs)
                 for (int pass = 0; pass < qp.cfg.passes && k < slots[i]; ++pass, ++k) {
                     const double cells = 2.0 * qp.cfg.G * qp.cfg.R * (double)d.shard.n_residues;
-                    fprintf(stderr, "osw trace: pair (%u,%u) G=%d R=%d pass %d/%d  %llu cycles  %.2f padded cells/SM-clk\n",
+                    fprintf(stderr, "osw trace: pair (%u,%u) G=%d R=%d pass %d/%d  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
                             qp.len_a, qp.len_b, qp.cfg.G, qp.cfg.R, pass + 1, qp.cfg.passes,
-                            (unsigned long long)d.h_cycles[k], cells / ((double)d.h_cycles[k] * d.n_sms));
+                            (unsigned long long)(d.h_cycles[k] / d.n_sms), cells / (double)d.h_cycles[k]);
                 }
         }
         const uint32_t r = (uint32_t)std::min<uint64_t>((uint64_t)top_r, N);

@@ -57,11 +57,36 @@ __global__ void __launch_bounds__(CAL_THREADS) calib_kernel(CalArgs g) {
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < 16; ++r) sc[r] = g.a + r;
+                for (int r = 0; r < 16; ++r) sc[r] = Hl[(r + 5) & 15] ^ g.a;     // any per-row value already in a register
             }
             uint32_t Hprev = 0;
+            if (MODE == 6 || MODE == 7) {
+                // signed variants: relu folded into the add-max, H by a 2-input max, packed 16-bit add
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    uint32_t t = __viaddmax_s16x2_relu(diag, sc[r], E[r]);
+                    uint32_t H = __vmaxs2(t, F);
+                    uint32_t u = __vadd2(H, g.ngoe);
+                    E[r] = __viaddmax_s16x2(E[r], g.nge, u);
+                    F = __viaddmax_s16x2(F, g.nge, u);
+                    diag = Hl[r];
+                    Hl[r] = H;
+                    if (MODE == 6) { if (r & 1) best = __vimax3_s16x2(best, Hprev, H); else Hprev = H; }
+                }
+                continue;
+            }
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
+                if (MODE == 8) {       // current arithmetic without the column-maximum tracking
+                    uint32_t t = __viaddmax_u16x2(diag, sc[r], E[r]);
+                    uint32_t H = __vimax3_u16x2(t, F, g.B);
+                    uint32_t u = H - g.ngoe;
+                    E[r] = __viaddmax_u16x2(E[r], g.nge, u);
+                    F = __viaddmax_u16x2(F, g.nge, u);
+                    diag = Hl[r];
+                    Hl[r] = H;
+                    continue;
+                }
                 uint32_t t = __viaddmax_u16x2(diag, sc[r], E[r]);
                 uint32_t H = __vimax3_u16x2(t, F, g.B);
                 uint32_t u = (MODE == 4) ? H - g.ngoe : imad_sub(H, g.one, g.ngoe);
@@ -106,7 +131,7 @@ int run_mode(int n_sms, CalArgs g, double *cycles_out) {
 
 }  // namespace
 
-extern "C" int osw_calibrate(int device, double out[8]) {
+extern "C" int osw_calibrate(int device, double out[12]) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return OSW_E_NODEV;
     if (cudaSetDevice(device) != cudaSuccess) return OSW_E_CUDA;
@@ -118,13 +143,16 @@ extern "C" int osw_calibrate(int device, double out[8]) {
     const double warp_instr = (double)(CAL_THREADS / 32) * CAL_ITERS;
     double cyc;
     int rc = 0;
-    for (int k = 0; k < 8; ++k) out[k] = 0;
+    for (int k = 0; k < 12; ++k) out[k] = 0;
     rc |= run_mode<0>(n_sms, g, &cyc); out[0] = warp_instr * 8 * 32 / cyc;            // thread-instr / SM-clk
     rc |= run_mode<1>(n_sms, g, &cyc); out[1] = warp_instr * 8 * 32 / cyc;
     rc |= run_mode<2>(n_sms, g, &cyc); out[2] = warp_instr * 16 * 2 * 32 / cyc;       // cells / SM-clk (IMAD form)
     rc |= run_mode<3>(n_sms, g, &cyc); out[3] = warp_instr * 8 * 32 / cyc;
     rc |= run_mode<4>(n_sms, g, &cyc); out[5] = warp_instr * 16 * 2 * 32 / cyc;       // compiler-chosen subtract
     rc |= run_mode<5>(n_sms, g, &cyc); out[6] = warp_instr * 16 * 2 * 32 / cyc;       // + LDS.128 profile reads
+    rc |= run_mode<6>(n_sms, g, &cyc); out[7] = warp_instr * 16 * 2 * 32 / cyc;       // signed relu variant
+    rc |= run_mode<7>(n_sms, g, &cyc); out[8] = warp_instr * 16 * 2 * 32 / cyc;       // ... without max tracking
+    rc |= run_mode<8>(n_sms, g, &cyc); out[9] = warp_instr * 16 * 2 * 32 / cyc;       // unsigned without max tracking
     clock_probe<<<1, 1>>>(g.cycles);
     unsigned long long cp[2] = {0, 1};
     if (cudaMemcpy(cp, g.cycles, sizeof cp, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -1;

@@ -48,7 +48,7 @@ struct U16Params {
     uint32_t         row0;       // first query row of this pass
     int              gap_open_extend, gap_extend;
     uint32_t        *chunk_counter;
-    unsigned long long *cycle_acc;   // [2] min start / max end clock64 of the launch (GPU-wide), or nullptr
+    unsigned long long *cycle_acc;   // sum over CTAs of their elapsed clock64 cycles (one CTA per SM), or nullptr
 };
 // Picks (G,R,passes) for a query length; returns padded rows.
 uint32_t osw_u16_plan(uint32_t query_len, U16Config *cfg);

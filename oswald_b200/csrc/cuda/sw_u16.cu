@@ -136,7 +136,8 @@ sw_u16_kernel(const KArgs a) {
     const uint32_t mail_up = mail_self - 16;     // lane-1's mailbox (unused when t == 0)
     const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(s_ring + (wib * GROUPS + grp) * RING);
     const uint32_t B2 = a.bias2, NGE = a.nge2, GOE2 = 0u - a.ngoe_word;
-    const bool multi_in = p.bound_in != nullptr;
+    const bool multi_in = p.bound_in != nullptr, has_out = p.bound_out != nullptr;
+    const uint32_t last_mask = t == G - 1 ? OSW_COL_LAST : 0u;
 
     for (;;) {
         // ---- fetch one chunk per group ---------------------------------------------------
@@ -191,6 +192,8 @@ sw_u16_kernel(const KArgs a) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) { diag[c] = B2; mid[c] = make_uint4(B2, B2, B2, OSW_COL_PADBYTE); }
         uint32_t seq = ck.seq0;
+        uint2 *out_base = has_out ? p.bound_out + ck.stream_off : nullptr;
+        const uint32_t out_limit = t == G - 1 ? cols_padded : 0u;      // only the group's last lane stores
         sts128(mail_self, make_uint4(B2, B2, B2, OSW_COL_PADBYTE));
         __syncwarp();
 
@@ -263,20 +266,18 @@ sw_u16_kernel(const KArgs a) {
                 const uint32_t lf = msg[NC - 1].w;
                 const uint32_t Hbot = Hl[R - 1], Fbot = F[NC - 1], cmbot = cm[NC - 1];
                 run = __vmaxu2(run, cmbot);
-                if (t == G - 1) {
-                    // column this lane's last segment just finished
-                    const uint32_t col = step - (NC * G - 1);
-                    if (p.bound_out && col < cols_padded)
-                        __stcg(p.bound_out + ck.stream_off + col, make_uint2(Hbot, Fbot));
-                    if (lf & OSW_COL_LAST) {
-                        const uint32_t lo = run & 0xffffu, hi = run >> 16;
-                        const int sa = lo >= FLAG_THRESHOLD ? OSW_SCORE_FLAGGED : (int)(lo - a.bias);
-                        const int sb = hi >= FLAG_THRESHOLD ? OSW_SCORE_FLAGGED : (int)(hi - a.bias);
-                        atomicMax(p.scores_a + seq, sa);
-                        if (p.scores_b) atomicMax(p.scores_b + seq, sb);
-                        ++seq;
-                        run = B2;
-                    }
+                if (has_out) {                       // (uniform) several passes: park this pass's bottom row
+                    const uint32_t col = step - (NC * G - 1);        // column the last segment just finished
+                    if (col < out_limit) __stcg(out_base + col, make_uint2(Hbot, Fbot));
+                }
+                if (lf & last_mask) {                // last lane of the group, last column of a sequence
+                    const uint32_t lo = run & 0xffffu, hi = run >> 16;
+                    const int sa = lo >= FLAG_THRESHOLD ? OSW_SCORE_FLAGGED : (int)(lo - a.bias);
+                    const int sb = hi >= FLAG_THRESHOLD ? OSW_SCORE_FLAGGED : (int)(hi - a.bias);
+                    atomicMax(p.scores_a + seq, sa);
+                    if (p.scores_b) atomicMax(p.scores_b + seq, sb);
+                    ++seq;
+                    run = B2;
                 }
                 __syncwarp();
                 sts128(mail_self, make_uint4(Hbot, Fbot, cmbot, lf));
@@ -286,7 +287,7 @@ sw_u16_kernel(const KArgs a) {
             __syncwarp();
         }
     }
-    if (p.cycle_acc && threadIdx.x == 0) atomicMax(p.cycle_acc, (unsigned long long)(clock64() - clk0));
+    if (p.cycle_acc && threadIdx.x == 0) atomicAdd(p.cycle_acc, (unsigned long long)(clock64() - clk0));
 }
 
 template <int G, int R>

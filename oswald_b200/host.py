@@ -220,11 +220,13 @@ def merge_hits(lists, top):
 
 
 def calibrate(device=0):
-    out = (C.c_double * 8)()
+    out = (C.c_double * 12)()
     capi.check(capi.lib().osw_calibrate(device, out), "osw_calibrate")
     return {"viaddmnmx_u16x2_per_sm_clk": out[0], "vimnmx3_u16x2_per_sm_clk": out[1],
             "cells_per_sm_clk_step_imad": out[2], "imad_per_sm_clk": out[3], "sm_mhz": out[4],
-            "cells_per_sm_clk_step_plain_sub": out[5], "cells_per_sm_clk_step_with_lds": out[6]}
+            "cells_per_sm_clk_step_plain_sub": out[5], "cells_per_sm_clk_step_with_lds": out[6],
+            "cells_per_sm_clk_step_signed_relu": out[7], "cells_per_sm_clk_step_signed_relu_nomax": out[8],
+            "cells_per_sm_clk_step_nomax": out[9]}
 
 
 MIX_CLASSES = ["VIADDMNMX.U16x2", "VIMNMX3.U16x2", "VIADD", "IMAD", "HMNMX2", "VIMNMX.U16x2", "VIMNMX.U32", "LOP3",
