@@ -295,11 +295,13 @@ int launch_one(const KArgs &a, int n_sms, cudaStream_t st) {
     constexpr int THREADS = block_threads(R);
     const size_t prof = prof_copy_bytes(G, R) * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0);
     const size_t smem = prof + (size_t)(THREADS / 32) * 32 * 16 + (size_t)(THREADS / 32) * (32 / G) * RING * 16;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};          // the attribute is per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return OSW_E_CUDA;
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         if (cudaFuncSetAttribute(sw_u16_kernel<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return OSW_E_CUDA;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     sw_u16_kernel<G, R><<<n_sms, THREADS, smem, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? OSW_OK : OSW_E_CUDA;

@@ -226,3 +226,19 @@ def test_cli_report_matches_the_reference(built, tmp_path):
                 assert [[int(l.split("\t")[0]), l.split("\t")[1]] for l in lines] == h["top"]
             dump = np.fromfile(tmp_path / "dump.bin", dtype=np.int32).reshape(-1, meta["n_seqs"])
             assert np.array_equal(dump, run["score_matrix"])
+
+
+def test_two_gpus_in_one_context(built):
+    """osw_init(2): the library deals chunks to both GPUs and merges their hit lists itself."""
+    import ctypes as C
+    n = C.c_int(0)
+    built.osw_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(31)
+    db = make_db(rand_seqs(rng, 4000, 10, 400))
+    q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (90, 250, 700)])
+    with ob.Searcher(2) as s:
+        s.load_db(db, max_chunk_residues=1024)
+        assert s.stats()["n_seqs"] == db.n_seqs
+        check(s, db, q, "blosum62", 10, 2, 10)
