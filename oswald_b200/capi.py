@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboswald_cuda.so")
+LIB_PATH = os.environ.get("OSWALD_CUDA_LIB") or os.path.join(_HERE, "liboswald_cuda.so")   # override: experiments only
 
 OSW_OK = 0
 OSW_K_U16, OSW_K_I32, OSW_K_DEFAULT = 1, 2, 3

@@ -318,28 +318,11 @@ extern "C" size_t osw_merge_hits(const osw_hit *const *lists, const uint32_t *co
 
 namespace {
 
-struct QueryPair { int a, b; uint32_t len_a, len_b; U16Config cfg; };
-
-// Pairs queries of similar length (longest first); with an odd count the shortest stays single.
-void plan_pairs(const uint32_t *q_off, int nq, std::vector<QueryPair> &pairs) {
-    std::vector<int> order(nq);
-    for (int i = 0; i < nq; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-        return q_off[x + 1] - q_off[x] > q_off[y + 1] - q_off[y];
-    });
-    for (int i = 0; i < nq; i += 2) {
-        QueryPair p;
-        p.a = order[i]; p.len_a = q_off[p.a + 1] - q_off[p.a];
-        if (i + 1 < nq) { p.b = order[i + 1]; p.len_b = q_off[p.b + 1] - q_off[p.b]; }
-        else { p.b = -1; p.len_b = 0; }
-        osw_u16_plan(std::max(p.len_a, p.len_b), &p.cfg);
-        pairs.push_back(p);
-    }
-}
+constexpr int MAX_PASSES = 2048;
 
 int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32_t *q_off, int nq,
                    const int8_t *matrix, int go, int ge, uint32_t top_r, bool want_all,
-                   const std::vector<QueryPair> &pairs, uint32_t *n_launch_slots, uint64_t *launches,
+                   const std::vector<OswPass> &passes, uint32_t *n_launch_slots, uint64_t *launches,
                    uint64_t *padded_cells) {
     const osw_shard &s = d.shard;
     const uint64_t N = s.n_seqs;
@@ -378,12 +361,10 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
         d.pairs_cap = (uint32_t)cap;
         flag_cap = d.pairs_cap;
         bool need_bound = false;
-        for (const QueryPair &p : pairs) need_bound |= p.cfg.passes > 1;
+        for (const OswPass &p : passes) need_bound |= p.has_in || p.has_out;
         if (need_bound && !d.d_bound[0]) {
-            for (int k = 0; k < 2; ++k) {
-                CK(cudaMalloc(&d.d_bound[k], (s.stream_bytes ? s.stream_bytes : 1) * sizeof(uint2)));
-                CK(cudaMemsetAsync(d.d_bound[k], 0, (s.stream_bytes ? s.stream_bytes : 1) * sizeof(uint2), d.st));
-            }
+            CK(cudaMalloc(&d.d_bound[0], (s.stream_bytes ? s.stream_bytes : 1) * sizeof(uint2)));
+            CK(cudaMemsetAsync(d.d_bound[0], 0, (s.stream_bytes ? s.stream_bytes : 1) * sizeof(uint2), d.st));
         }
     }
 
@@ -399,42 +380,25 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
 
     uint32_t slot = 0;
     if (use_u16 && N) {
-        // Query pairs alternate between two streams: a launch is one persistent CTA per SM, so the
-        // next pair's CTAs move onto SMs as the previous launch's tail frees them.  Each stream has
-        // its own bottom-row buffer, updated in place (a warp writes a chunk's columns behind the
-        // ones it still has to read).
-        CK(cudaEventRecord(d.ev_fork, d.st));
-        CK(cudaStreamWaitEvent(d.st2, d.ev_fork, 0));
-        int pair_no = 0;
-        for (const QueryPair &qp : pairs) {
-            const int lane_no = pair_no++ & 1;
-            cudaStream_t lane_st = lane_no ? d.st2 : d.st;
-            const uint32_t rows_per_pass = (uint32_t)(qp.cfg.G * qp.cfg.R);
-            for (int pass = 0; pass < qp.cfg.passes; ++pass) {
-                if (slot >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
-                U16Params up;
-                up.stream = d.d_stream; up.chunks = d.d_chunks; up.n_chunks = s.n_chunks;
-                up.query_a = d.d_queries + q_off[qp.a]; up.len_a = qp.len_a;
-                up.query_b = qp.b >= 0 ? d.d_queries + q_off[qp.b] : d.d_queries; up.len_b = qp.len_b;
-                up.matrix = d.d_matrix;
-                up.scores_a = d.d_scores + (size_t)qp.a * N;
-                up.scores_b = qp.b >= 0 ? d.d_scores + (size_t)qp.b * N : nullptr;
-                up.bound_in = pass > 0 ? d.d_bound[lane_no] : nullptr;
-                up.bound_out = pass + 1 < qp.cfg.passes ? d.d_bound[lane_no] : nullptr;
-                up.row0 = (uint32_t)pass * rows_per_pass;
-                up.gap_open_extend = go + ge; up.gap_extend = ge;
-                up.chunk_counter = d.d_counters + 1 + slot;
-                up.cycle_acc = d.d_cycles + slot;
-                if ((rc = osw_launch_u16(up, qp.cfg, d.n_sms, lane_st)) != OSW_OK) {
-                    cuda_fail(cudaGetLastError(), "sw_u16 launch", __LINE__);
-                    return rc;
-                }
-                ++slot; ++*launches;
-                *padded_cells += (uint64_t)rows_per_pass * 2 * s.n_residues;
+        // One launch per pass, in order: a pass reads the bottom row the previous one parked (in
+        // place: a warp writes a chunk's columns behind the ones it still has to read).
+        for (const OswPass &ps : passes) {
+            if (slot >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
+            U16Params up;
+            up.stream = d.d_stream; up.chunks = d.d_chunks; up.n_chunks = s.n_chunks;
+            up.queries = d.d_queries; up.q_off = d.d_qoff; up.matrix = d.d_matrix;
+            up.scores = d.d_scores; up.n_seqs = N;
+            up.bound = d.d_bound[0];
+            up.gap_open_extend = go + ge; up.gap_extend = ge;
+            up.chunk_counter = d.d_counters + 1 + slot;
+            up.cycle_acc = d.d_cycles + slot;
+            if ((rc = osw_launch_u16(up, ps, d.n_sms, d.st)) != OSW_OK) {
+                cuda_fail(cudaGetLastError(), "sw_u16 launch", __LINE__);
+                return rc;
             }
+            ++slot; ++*launches;
+            *padded_cells += (uint64_t)ps.G * ps.R * 2 * s.n_residues;
         }
-        CK(cudaEventRecord(d.ev_join, d.st2));
-        CK(cudaStreamWaitEvent(d.st, d.ev_join, 0));
         CK(cudaEventRecord(d.ev[1], d.st));
         *launches += osw_collect_flagged(d.d_scores, N, nq, d.d_pairs, d.d_counters, flag_cap, d.st);
         CK(cudaMemcpyAsync(d.h_counts, d.d_counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, d.st));
@@ -457,8 +421,15 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
     for (int q = 0; q < nq; ++q)
         if (q_off[q + 1] < q_off[q] || q_off[q + 1] - q_off[q] > OSW_MAX_QUERY_LEN) return OSW_E_ARG;
     const double t_wall0 = now_ms();
-    std::vector<QueryPair> pairs;
-    plan_pairs(q_off, nq, pairs);
+    std::vector<OswPass> passes;
+    if (c->kernel_mask & OSW_K_U16) {
+        std::vector<uint32_t> q_len((size_t)nq);
+        for (int q = 0; q < nq; ++q) q_len[q] = q_off[q + 1] - q_off[q];
+        passes.resize(MAX_PASSES);
+        const int n_pass = osw_plan_passes(q_len.data(), nq, passes.data(), MAX_PASSES);
+        if (n_pass < 0) { snprintf(g_err, sizeof g_err, "the queries need more than %d passes", MAX_PASSES); return OSW_E_ARG; }
+        passes.resize((size_t)n_pass);
+    }
     const bool use_u16 = (c->kernel_mask & OSW_K_U16) != 0;
     uint64_t launches = 0, padded = 0, rescored = 0;
     std::vector<uint32_t> slots((size_t)c->n_dev, 0u);
@@ -466,7 +437,7 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
     // ---- phase 1: first stage on every GPU ------------------------------------------------
     for (int i = 0; i < c->n_dev; ++i) {
         int rc = enqueue_search(c, c->devs[i], queries, q_off, nq, matrix, go, ge, (uint32_t)top_r,
-                                all_scores != nullptr, pairs, &slots[i], &launches, &padded);
+                                all_scores != nullptr, passes, &slots[i], &launches, &padded);
         if (rc != OSW_OK) return rc;
     }
     const double t_h2d = now_ms();
@@ -533,14 +504,13 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
         if (i == 0) for (uint32_t k = 0; k < slots[i]; ++k) tm.sm_cycles += d.h_cycles[k];
         if (i == 0 && getenv("OSW_TRACE")) {
             // per-launch report: geometry, elapsed SM cycles, padded cell updates per SM-cycle
-            uint32_t k = 0;
-            for (const QueryPair &qp : pairs)
-                for (int pass = 0; pass < qp.cfg.passes && k < slots[i]; ++pass, ++k) {
-                    const double cells = 2.0 * qp.cfg.G * qp.cfg.R * (double)d.shard.n_residues;
-                    fprintf(stderr, "osw trace: pair (%u,%u) G=%d R=%d pass %d/%d  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
-                            qp.len_a, qp.len_b, qp.cfg.G, qp.cfg.R, pass + 1, qp.cfg.passes,
-                            (unsigned long long)(d.h_cycles[k] / d.n_sms), cells / (double)d.h_cycles[k]);
-                }
+            for (uint32_t k = 0; k < slots[i] && k < passes.size(); ++k) {
+                const OswPass &ps = passes[k];
+                const double cells = 2.0 * ps.G * ps.R * (double)d.shard.n_residues;
+                fprintf(stderr, "osw trace: pass %u/%zu G=%d R=%d in=%d out=%d  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
+                        k + 1, passes.size(), ps.G, ps.R, ps.has_in, ps.has_out,
+                        (unsigned long long)(d.h_cycles[k] / d.n_sms), cells / (double)d.h_cycles[k]);
+            }
         }
         const uint32_t r = (uint32_t)std::min<uint64_t>((uint64_t)top_r, N);
         per_dev[i].resize((size_t)nq * r);

@@ -30,30 +30,43 @@ void osw_launch_i32(const I32Params &p, int n_blocks, cudaStream_t st);
 int  osw_i32_block_threads();
 
 // ---- packed 16-bit DPX kernel (sw_u16.cu) ------------------------------------------------
-struct U16Config {       // geometry of one launch: G lanes per sequence, R rows per lane
-    int G, R, passes;
+// A launch ("pass") runs G lanes x R rows per database sequence in each 16-bit half of the
+// packed words.  The rows of a half are a stretch of that half's TRACK: the queries assigned
+// to the half, laid end to end with every query starting on a lane boundary.  A lane therefore
+// belongs to exactly one query per half.
+#define OSW_LANE_START 1u    // the lane holds the query's first row: its input from above is "no row" (zeros)
+#define OSW_LANE_EMIT  2u    // the lane is the last one of its query in this pass: it publishes the maximum
+struct OswLaneDesc {
+    uint32_t query;      // index of the query (score row), or 0xffffffff for an idle lane
+    uint32_t q_len;      // its length (0 for an idle lane)
+    uint32_t row0;       // first row of the query held by this lane in this pass
+    uint32_t flags;      // OSW_LANE_*
 };
+struct OswPass {
+    int G, R;
+    OswLaneDesc lane[2][32];   // [half][lane of group]
+    int has_in;          // some half continues a query from the previous pass (bottom-row hand-over)
+    int has_out;         // some half's last lane holds a query that continues in the next pass
+};
+// Lays the queries out on two tracks and cuts the tracks into passes.  Returns the number of
+// passes (<= max_passes), or -1 if they do not fit.  Exported for the tests.
+extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes);
+
 struct U16Params {
     const uint8_t   *stream;
     const osw_chunk *chunks;     // descending-length order
     uint32_t         n_chunks;
-    const uint8_t   *query_a;    // rows of query A / B (codes); rows >= length read as pad
-    const uint8_t   *query_b;
-    uint32_t         len_a, len_b;
+    const uint8_t   *queries;    // all queries back to back (codes)
+    const uint32_t  *q_off;      // [nq+1]
     const int8_t    *matrix;
-    int32_t         *scores_a;   // [n_seqs] rows of the score matrix for the two queries
-    int32_t         *scores_b;   // (scores_b may be nullptr when the pair has one query)
-    const uint2     *bound_in;   // [stream_bytes] (H,F) bottom row of the previous pass, or nullptr
-    uint2           *bound_out;  // [stream_bytes] bottom row of this pass, or nullptr on the last pass
-    uint32_t         row0;       // first query row of this pass
+    int32_t         *scores;     // [nq][n_seqs]
+    uint64_t         n_seqs;
+    uint2           *bound;      // [stream_bytes] (H,F) bottom row handed from pass to pass, in place; or nullptr
     int              gap_open_extend, gap_extend;
     uint32_t        *chunk_counter;
     unsigned long long *cycle_acc;   // sum over CTAs of their elapsed clock64 cycles (one CTA per SM), or nullptr
 };
-// Picks (G,R,passes) for a query length; returns padded rows.
-uint32_t osw_u16_plan(uint32_t query_len, U16Config *cfg);
-size_t   osw_u16_smem_bytes(const U16Config &cfg);
-int      osw_launch_u16(const U16Params &p, const U16Config &cfg, int n_sms, cudaStream_t st);
+int osw_launch_u16(const U16Params &p, const OswPass &pass, int n_sms, cudaStream_t st);
 
 // ---- device top-r (topr.cu) --------------------------------------------------------------
 struct TopRWork {            // per-device scratch, sized for nq_max queries

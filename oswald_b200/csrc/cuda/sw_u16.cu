@@ -4,10 +4,12 @@
 // :937-1030, and the FPGA kernel device/sw.cl) - not their structure.
 //
 // Work decomposition
-//   * A launch scores ONE PAIR of queries (A in the low, B in the high 16 bits of every
-//     32-bit word) over `G*R` consecutive query rows against every database chunk.  Both
-//     halves see the same database residue, so one shared-memory read of the pair profile
-//         prof[residue][row] = (M[A[row]][residue], M[B[row]][residue])
+//   * Every 32-bit word carries two independent DP problems against the SAME database residue:
+//     the low half works on rows of track 0, the high half on rows of track 1 (plan.cu lays the
+//     queries end to end on the two tracks, each query starting on a lane boundary).  A launch
+//     ("pass") covers the next `G*R` rows of both tracks against every database chunk.  One
+//     shared-memory read of the pair profile
+//         prof[residue][row] = (M[track0[row]][residue], M[track1[row]][residue])
 //     serves two cell updates and is bank-conflict free by construction (see below).
 //   * G lanes (4, 8, 16 or 32) form a systolic array over the query rows: lane t owns rows
 //     t*R .. t*R+R-1, with H(left), E of its rows in registers.  A chunk's column stream flows
@@ -34,6 +36,8 @@
 // whose biased maximum reaches 65504 may have wrapped and is flagged for the 32-bit kernel
 // (scores grow by at most 17 per cell, so a wrap cannot be missed).
 #include "osw_internal.h"
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -47,14 +51,12 @@ __host__ __device__ constexpr size_t prof_copy_bytes(int G, int R) { return (siz
 __host__ __device__ constexpr int block_threads(int R) { return R > 36 ? 384 : 512; }
 // A lane's R rows are swept as NUM_CHAINS independent segments (segment c works one column
 // behind segment c-1): two dependency chains per thread keep the DPX pipe fed.
-constexpr int NUM_CHAINS = 2;
+#ifndef OSW_NUM_CHAINS
+#define OSW_NUM_CHAINS 2
+#endif
+constexpr int NUM_CHAINS = OSW_NUM_CHAINS;
 __host__ __device__ constexpr int seg_begin(int R, int NC, int c) { return ((R / 4) * c + NC - 1) / NC; }   // first quad of segment c
 
-__device__ __forceinline__ uint32_t imad_add(uint32_t h, uint32_t one, uint32_t c) {
-    uint32_t u;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(u) : "r"(h), "r"(one), "r"(c));
-    return u;
-}
 // mailbox / ring traffic: ordered against __syncwarp
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
@@ -73,17 +75,17 @@ __device__ __forceinline__ uint4 lds128_const(uint32_t addr) {
 
 struct KArgs {
     U16Params p;
-    uint32_t one;            // 1, opaque to the compiler (forces IMAD for the subtract)
+    OswLaneDesc lane[2][32]; // [half][lane of group]: which query rows the lane holds
+    uint32_t has_in, has_out;
     uint32_t bias2;          // B | B<<16
     uint32_t nge2;           // (-ge) & 0xffff, both halves
     uint32_t ngoe_word;      // -(goe | goe<<16) as a 32-bit two's complement
     uint32_t bias;           // B
 };
 
-template <int G, int R>
-__global__ void __launch_bounds__(block_threads(R), 1)
+template <int G, int R, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 sw_u16_kernel(const KArgs a) {
-    constexpr int THREADS = block_threads(R);
     constexpr int WARPS = THREADS / 32;
     constexpr int GROUPS = 32 / G;              // groups per warp
     constexpr int P = pitch_quads(R);
@@ -116,11 +118,13 @@ sw_u16_kernel(const KArgs a) {
         const int tt = slot / P, k = slot % P;
         uint32_t w[4] = {0, 0, 0, 0};
         if (tt < G && k < R / 4) {
-#pragma unroll
+            const OswLaneDesc da = a.lane[0][tt], db = a.lane[1][tt];
+            const uint8_t *qa = da.q_len ? p.queries + p.q_off[da.query] : p.queries;
+            const uint8_t *qb = db.q_len ? p.queries + p.q_off[db.query] : p.queries;
             for (int r = 0; r < 4; ++r) {
-                const uint32_t row = p.row0 + tt * R + 4 * k + r;
-                const int ca = row < p.len_a ? p.query_a[row] : OSW_PAD_CODE;
-                const int cb = row < p.len_b ? p.query_b[row] : OSW_PAD_CODE;
+                const uint32_t ra = da.row0 + 4 * k + r, rb = db.row0 + 4 * k + r;
+                const int ca = ra < da.q_len ? qa[ra] : OSW_PAD_CODE;
+                const int cb = rb < db.q_len ? qb[rb] : OSW_PAD_CODE;
                 w[r] = ((uint32_t)s_mat[ca * 32 + b] & 0xffffu) | ((uint32_t)s_mat[cb * 32 + b] << 16);
             }
         }
@@ -136,8 +140,13 @@ sw_u16_kernel(const KArgs a) {
     const uint32_t mail_up = mail_self - 16;     // lane-1's mailbox (unused when t == 0)
     const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(s_ring + (wib * GROUPS + grp) * RING);
     const uint32_t B2 = a.bias2, NGE = a.nge2, GOE2 = 0u - a.ngoe_word;
-    const bool multi_in = p.bound_in != nullptr, has_out = p.bound_out != nullptr;
-    const uint32_t last_mask = t == G - 1 ? OSW_COL_LAST : 0u;
+    const bool multi_in = a.has_in != 0, has_out = a.has_out != 0;
+    // what this lane is, per half: first lane of a query (its input from above is replaced by
+    // "no row"), last lane of a query in this pass (it publishes that query's maximum)
+    const uint32_t fa = a.lane[0][t].flags, fb = a.lane[1][t].flags;
+    const uint32_t keep = ((fa & OSW_LANE_START) ? 0u : 0x0000ffffu) | ((fb & OSW_LANE_START) ? 0u : 0xffff0000u);
+    const uint32_t emit = ((fa & OSW_LANE_EMIT) && a.lane[0][t].q_len ? 1u : 0u) | ((fb & OSW_LANE_EMIT) && a.lane[1][t].q_len ? 2u : 0u);
+    const uint32_t last_mask = emit ? OSW_COL_LAST : 0u;
 
     for (;;) {
         // ---- fetch one chunk per group ---------------------------------------------------
@@ -155,7 +164,7 @@ sw_u16_kernel(const KArgs a) {
         for (int o = 16; o; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
         const uint32_t n_blocks = (steps + 31) / 32;
         const uint8_t *col_src = p.stream + ck.stream_off + t * EPL;
-        const uint2 *bnd_src = multi_in ? p.bound_in + ck.stream_off + t * EPL : nullptr;
+        const uint2 *bnd_src = multi_in ? p.bound + ck.stream_off + t * EPL : nullptr;
         const uint32_t cols_padded = have ? (ck.n_cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN : 0;
 
         // ring fill helpers: block b covers columns [32b, 32b+32); this lane fills EPL of them
@@ -192,7 +201,7 @@ sw_u16_kernel(const KArgs a) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) { diag[c] = B2; mid[c] = make_uint4(B2, B2, B2, OSW_COL_PADBYTE); }
         uint32_t seq = ck.seq0;
-        uint2 *out_base = has_out ? p.bound_out + ck.stream_off : nullptr;
+        uint2 *out_base = has_out ? p.bound + ck.stream_off : nullptr;
         const uint32_t out_limit = t == G - 1 ? cols_padded : 0u;      // only the group's last lane stores
         sts128(mail_self, make_uint4(B2, B2, B2, OSW_COL_PADBYTE));
         __syncwarp();
@@ -205,6 +214,11 @@ sw_u16_kernel(const KArgs a) {
                 const uint32_t in_addr = t == 0 ? ring_base + (step & (RING - 1)) * 16 : mail_up;
                 uint4 msg[NC];
                 msg[0] = lds128(in_addr);
+#ifndef OSW_EXPERIMENT_NO_KEEP
+                msg[0].x = (msg[0].x & keep) | (B2 & ~keep);      // a query's first lane has no row above it
+                msg[0].y = (msg[0].y & keep) | (B2 & ~keep);
+                msg[0].z = (msg[0].z & keep) | (B2 & ~keep);
+#endif
 #pragma unroll
                 for (int c = 1; c < NC; ++c) msg[c] = mid[c];
                 uint32_t paddr[NC];
@@ -274,8 +288,8 @@ sw_u16_kernel(const KArgs a) {
                     const uint32_t lo = run & 0xffffu, hi = run >> 16;
                     const int sa = lo >= FLAG_THRESHOLD ? OSW_SCORE_FLAGGED : (int)(lo - a.bias);
                     const int sb = hi >= FLAG_THRESHOLD ? OSW_SCORE_FLAGGED : (int)(hi - a.bias);
-                    atomicMax(p.scores_a + seq, sa);
-                    if (p.scores_b) atomicMax(p.scores_b + seq, sb);
+                    if (emit & 1u) atomicMax(p.scores + (size_t)a.lane[0][t].query * p.n_seqs + seq, sa);
+                    if (emit & 2u) atomicMax(p.scores + (size_t)a.lane[1][t].query * p.n_seqs + seq, sb);
                     ++seq;
                     run = B2;
                 }
@@ -290,21 +304,31 @@ sw_u16_kernel(const KArgs a) {
     if (p.cycle_acc && threadIdx.x == 0) atomicAdd(p.cycle_acc, (unsigned long long)(clock64() - clk0));
 }
 
-template <int G, int R>
-int launch_one(const KArgs &a, int n_sms, cudaStream_t st) {
-    constexpr int THREADS = block_threads(R);
+template <int G, int R, int THREADS>
+int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
     const size_t prof = prof_copy_bytes(G, R) * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0);
     const size_t smem = prof + (size_t)(THREADS / 32) * 32 * 16 + (size_t)(THREADS / 32) * (32 / G) * RING * 16;
     static bool configured[64] = {};          // the attribute is per device
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return OSW_E_CUDA;
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        if (cudaFuncSetAttribute(sw_u16_kernel<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(sw_u16_kernel<G, R, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return OSW_E_CUDA;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    sw_u16_kernel<G, R><<<n_sms, THREADS, smem, st>>>(a);
+    sw_u16_kernel<G, R, THREADS><<<n_sms, THREADS, smem, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? OSW_OK : OSW_E_CUDA;
+}
+
+// CTA size: 512 threads (128 registers each) up to R = 36, 384 (168 registers) above.
+// OSW_THREADS=256|384 overrides for experiments.
+template <int G, int R>
+int launch_one(const KArgs &a, int n_sms, cudaStream_t st) {
+    static int forced = -1;
+    if (forced < 0) { const char *e = getenv("OSW_THREADS"); forced = e ? atoi(e) : 0; }
+    if (forced == 256) return launch_threads<G, R, 256>(a, n_sms, st);
+    if (forced == 384 || R > 36) return launch_threads<G, R, 384>(a, n_sms, st);
+    return launch_threads<G, R, 512>(a, n_sms, st);
 }
 
 template <int G>
@@ -324,43 +348,24 @@ int launch_g(int R, const KArgs &a, int n_sms, cudaStream_t st) {
 
 }  // namespace
 
-// Geometry for a query of `query_len` rows: minimise passes*G*(R+3) (3 = per-column overhead
-// in row equivalents) subject to passes*G*R >= query_len; several passes only with G = 32.
-uint32_t osw_u16_plan(uint32_t query_len, U16Config *cfg) {
-    static const int Gs[4] = {4, 8, 16, 32};
-    static const int Rs[8] = {16, 20, 24, 28, 32, 36, 40, 44};
-    uint64_t best_cost = ~0ull;
-    U16Config best = {32, 44, 1};
-    if (query_len == 0) query_len = 1;
-    for (int gi = 0; gi < 4; ++gi)
-        for (int ri = 0; ri < 8; ++ri) {
-            const int G = Gs[gi], R = Rs[ri];
-            uint32_t passes = (query_len + G * R - 1) / (G * R);
-            if (passes > 1 && G != 32) continue;
-            uint64_t cost = (uint64_t)passes * G * (R + 3);
-            if (cost < best_cost || (cost == best_cost && (int)passes < best.passes)) {
-                best_cost = cost; best.G = G; best.R = R; best.passes = (int)passes;
-            }
-        }
-    *cfg = best;
-    return (uint32_t)(best.passes * best.G * best.R);
-}
-
-int osw_launch_u16(const U16Params &p, const U16Config &cfg, int n_sms, cudaStream_t st) {
+int osw_launch_u16(const U16Params &p, const OswPass &pass, int n_sms, cudaStream_t st) {
     KArgs a;
     a.p = p;
-    a.one = 1u;
+    memcpy(a.lane, pass.lane, sizeof a.lane);
+    a.has_in = pass.has_in && p.bound ? 1u : 0u;
+    a.has_out = pass.has_out && p.bound ? 1u : 0u;
+    if ((pass.has_in || pass.has_out) && !p.bound) return OSW_E_ARG;
     const uint32_t goe = (uint32_t)p.gap_open_extend, ge = (uint32_t)p.gap_extend;
     const uint32_t B = goe + ge + 32u;
     a.bias = B; a.bias2 = B | (B << 16);
     const uint32_t nge = (0x10000u - ge) & 0xffffu;
     a.nge2 = nge | (nge << 16);
     a.ngoe_word = 0u - (goe | (goe << 16));
-    switch (cfg.G) {
-        case 4:  return launch_g<4>(cfg.R, a, n_sms, st);
-        case 8:  return launch_g<8>(cfg.R, a, n_sms, st);
-        case 16: return launch_g<16>(cfg.R, a, n_sms, st);
-        case 32: return launch_g<32>(cfg.R, a, n_sms, st);
+    switch (pass.G) {
+        case 4:  return launch_g<4>(pass.R, a, n_sms, st);
+        case 8:  return launch_g<8>(pass.R, a, n_sms, st);
+        case 16: return launch_g<16>(pass.R, a, n_sms, st);
+        case 32: return launch_g<32>(pass.R, a, n_sms, st);
     }
     return OSW_E_ARG;
 }

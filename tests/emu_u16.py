@@ -2,17 +2,21 @@
 
 TEST INFRASTRUCTURE.  Pure Python, tiny inputs only.  It follows the kernel step by step -
 column stream with FIRST/LAST flags, per-lane mailbox messages {H, F, column max, residue+flags},
-lane t working on column (step - t), biased unsigned 16-bit arithmetic with wrap-around,
-per-pass bottom-row hand-over, flagging at 65504 - so that the scheme itself (not the CUDA
-code) can be checked against the oracle on the CPU.  One 16-bit half is modelled (the two
-halves of a word are independent).
+station k working on column (step - k), biased unsigned 16-bit arithmetic with wrap-around,
+per-pass bottom-row hand-over, lanes that start / end a query inside a pass, flagging at 65504 -
+so that the scheme itself (not the CUDA code) can be checked against the oracle on the CPU.
+One 16-bit half is modelled (the two halves of a word are independent); a lane with `chains`
+row segments is `chains` consecutive stations.
 """
+import ctypes as C
+
 import numpy as np
 
 FIRST, LAST, PAD = 0x20, 0x40, 23
 THRESH = 65504
 FLAGGED = 0x7FFFFFFF
 M16 = 0xFFFF
+LANE_START, LANE_EMIT = 1, 2
 
 
 def build_stream(seqs):
@@ -33,29 +37,18 @@ def segment_rows(R, chains):
     return [4 * (begin[c + 1] - begin[c]) for c in range(chains)]
 
 
-def run_pass(stream, n_seqs, query, row0, G, R, mat, go, ge, bound_in, want_out, scores, chains=1):
-    """One launch: rows row0 .. row0+G*R-1 of `query` against the chunk `stream`.  With
-    chains > 1 every lane is `chains` consecutive stations of the systolic array (its row
-    segments), each one column behind the previous one."""
+def run_pass(stream, n_seqs, stations, mat, go, ge, bound_in, want_out, scores):
+    """One launch.  stations: list of dicts {rows: [codes], start: bool, emit: query index or None}.
+    scores: dict query -> list of per-sequence scores (max-accumulated)."""
     goe = go + ge
     B = goe + ge + 32
     nge = (0x10000 - ge) & M16
-    if chains > 1:
-        seg = segment_rows(R, chains)
-        stations, first = [], row0
-        for t in range(G):
-            for n_rows in seg:
-                stations.append([(int(query[first + r]) if first + r < len(query) else PAD) for r in range(n_rows)])
-                first += n_rows
-        rows = stations
-        G = len(rows)
-    else:
-        rows = [[(int(query[row0 + t * R + r]) if row0 + t * R + r < len(query) else PAD) for r in range(R)] for t in range(G)]
-    Hl = [[B] * len(rows[t]) for t in range(G)]
-    E = [[B] * len(rows[t]) for t in range(G)]
+    G = len(stations)
+    Hl = [[B] * len(st["rows"]) for st in stations]
+    E = [[B] * len(st["rows"]) for st in stations]
     diag_top = [B] * G
-    run = B
-    seq = 0
+    run = [B] * G
+    seq = [0] * G
     mail = [(B, B, B, PAD)] * G
     n = len(stream)
     bound_out = [None] * n if want_out else None
@@ -71,14 +64,17 @@ def run_pass(stream, n_seqs, query, row0, G, R, mat, go, ge, bound_in, want_out,
             else:
                 msg = mail[t - 1]
             hup, fup, cm, lf = msg
+            if stations[t]["start"]:
+                hup, fup, cm = B, B, B
             if lf & FIRST:
-                Hl[t] = [B] * len(rows[t])
-                E[t] = [B] * len(rows[t])
+                Hl[t] = [B] * len(Hl[t])
+                E[t] = [B] * len(E[t])
                 diag_top[t] = B
             code = lf & 31
             F, diag = fup, diag_top[t]
-            for r in range(len(rows[t])):
-                sc = int(mat[rows[t][r] * 32 + code]) & M16
+            rows = stations[t]["rows"]
+            for r in range(len(rows)):
+                sc = int(mat[rows[r] * 32 + code]) & M16
                 tt = max((diag + sc) & M16, E[t][r])
                 H = max(tt, F, B)
                 u = (H - goe) & M16
@@ -88,29 +84,81 @@ def run_pass(stream, n_seqs, query, row0, G, R, mat, go, ge, bound_in, want_out,
                 Hl[t][r] = H
                 cm = max(cm, H)
             diag_top[t] = hup
-            if t == G - 1:
-                run = max(run, cm)
+            run[t] = max(run[t], cm)
+            if t == G - 1 and want_out:
                 col = step - (G - 1)
-                if want_out and 0 <= col < n:
+                if 0 <= col < n:
                     bound_out[col] = (Hl[t][-1], F)
-                if lf & LAST:
-                    val = FLAGGED if run >= THRESH else run - B
-                    scores[seq] = max(scores[seq], val)
-                    seq += 1
-                    run = B
+            if (lf & LAST) and stations[t]["emit"] is not None:
+                val = FLAGGED if run[t] >= THRESH else run[t] - B
+                row = scores[stations[t]["emit"]]
+                row[seq[t]] = max(row[seq[t]], val)
+                seq[t] += 1
+                run[t] = B
             new_mail[t] = (Hl[t][-1], F, cm, lf)
         mail = new_mail
-    assert seq == n_seqs
+    for t in range(G):
+        assert stations[t]["emit"] is None or seq[t] == n_seqs
     return bound_out
 
 
 def score_chunk(seqs, query, G, R, mat, go, ge, chains=1):
-    """Scores of `query` against every sequence of one chunk (FLAGGED where the kernel would flag)."""
+    """One query alone, rows dealt G*R per pass (the simplest plan)."""
     stream = build_stream(seqs)
     n_seqs = sum(1 for s in seqs if len(s))
-    scores = [0] * n_seqs
+    scores = {0: [0] * n_seqs}
     passes = max(1, -(-len(query) // (G * R)))
+    seg = segment_rows(R, chains)
     bound = None
     for p in range(passes):
-        bound = run_pass(stream, n_seqs, query, p * G * R, G, R, mat, go, ge, bound, p + 1 < passes, scores, chains)
-    return np.array(scores, dtype=np.int64)
+        stations, first = [], p * G * R
+        for t in range(G):
+            for c, n_rows in enumerate(seg):
+                rows = [(int(query[first + r]) if first + r < len(query) else PAD) for r in range(n_rows)]
+                stations.append({"rows": rows, "start": p == 0 and t == 0 and c == 0,
+                                 "emit": 0 if (t == G - 1 and c == len(seg) - 1) else None})
+                first += n_rows
+        bound = run_pass(stream, n_seqs, stations, mat, go, ge, bound, p + 1 < passes, scores)
+    return np.array(scores[0], dtype=np.int64)
+
+
+# ---- the product's planner (plan.cu), through ctypes ----------------------------------------
+class LaneDesc(C.Structure):
+    _fields_ = [("query", C.c_uint32), ("q_len", C.c_uint32), ("row0", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class Pass(C.Structure):
+    _fields_ = [("G", C.c_int), ("R", C.c_int), ("lane", (LaneDesc * 32) * 2), ("has_in", C.c_int), ("has_out", C.c_int)]
+
+
+def plan_passes(lib, q_lens, max_passes=256):
+    lib.osw_plan_passes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.osw_plan_passes.restype = C.c_int
+    arr = (C.c_uint32 * len(q_lens))(*q_lens)
+    out = (Pass * max_passes)()
+    n = lib.osw_plan_passes(arr, len(q_lens), out, max_passes)
+    assert n >= 0
+    return [out[i] for i in range(n)]
+
+
+def score_with_plan(passes, seqs, queries, mat, go, ge, chains=2):
+    """All queries against one chunk, following the planner's passes for both halves."""
+    stream = build_stream(seqs)
+    n_seqs = sum(1 for s in seqs if len(s))
+    scores = {q: [0] * n_seqs for q in range(len(queries))}
+    for half in (0, 1):
+        bound = None
+        for p in passes:
+            seg = segment_rows(p.R, chains)
+            stations = []
+            for t in range(p.G):
+                d = p.lane[half][t]
+                first = d.row0
+                for c, n_rows in enumerate(seg):
+                    q = queries[d.query] if d.q_len else []
+                    rows = [(int(q[first + r]) if first + r < d.q_len else PAD) for r in range(n_rows)]
+                    stations.append({"rows": rows, "start": bool(d.flags & LANE_START) and c == 0,
+                                     "emit": d.query if (d.flags & LANE_EMIT) and d.q_len and c == len(seg) - 1 else None})
+                    first += n_rows
+            bound = run_pass(stream, n_seqs, stations, mat, go, ge, bound if p.has_in else None, bool(p.has_out), scores)
+    return np.array([scores[q] for q in range(len(queries))], dtype=np.int64)

@@ -191,3 +191,60 @@ def test_cli_rejects_bad_options(built):
     assert subprocess.run([cli, "-O", "search", "-q", "x", "-d", "y", "-s", "blosum99"], capture_output=True).returncode != 0
     assert subprocess.run([cli, "-O", "search", "-q", "x", "-d", "y", "-g", "300"], capture_output=True).returncode != 0
     assert subprocess.run([cli, "-O", "bogus"], capture_output=True).returncode != 0
+
+
+def test_pass_planner_layout(built):
+    """plan.cu: every query row is covered exactly once, in order, on one track; queries start on
+    lane boundaries; START/EMIT flags are where the kernel needs them."""
+    rng = np.random.default_rng(8)
+    cases = [[144], [144, 189], [5, 37, 144, 189], [1, 1, 2], [0, 7, 0], [1000, 1500], [2005], [1537, 3005],
+             [144, 189, 222, 375, 464, 567, 657, 727, 850, 1000, 1500, 2005, 2504, 3005, 3564, 4061, 4548, 4743, 5147, 5478],
+             [65535], [65535, 1]] + [list(rng.integers(1, 3000, size=rng.integers(1, 12))) for _ in range(20)]
+    for lens in cases:
+        passes = emu_u16.plan_passes(built, [int(x) for x in lens], 4096)
+        covered = {q: 0 for q in range(len(lens))}
+        track_of = {}
+        for pi, p in enumerate(passes):
+            assert p.G in (4, 8, 16, 32) and p.R in (16, 20, 24, 28, 32, 36, 40, 44)
+            assert pi == 0 or p.G == 32
+            for half in (0, 1):
+                for t in range(p.G):
+                    d = p.lane[half][t]
+                    if d.q_len == 0:
+                        continue
+                    assert d.q_len == lens[d.query]
+                    assert track_of.setdefault(d.query, half) == half
+                    assert d.row0 == covered[d.query]                      # contiguous, in order
+                    assert bool(d.flags & emu_u16.LANE_START) == (d.row0 == 0)
+                    covered[d.query] += p.R
+                    ends_here = covered[d.query] >= d.q_len
+                    nxt = p.lane[half][t + 1] if t + 1 < p.G else None
+                    last_of_query_in_pass = nxt is None or nxt.q_len == 0 or nxt.query != d.query
+                    assert bool(d.flags & emu_u16.LANE_EMIT) == last_of_query_in_pass
+                    assert not ends_here or last_of_query_in_pass
+                # continuation flags
+                first, last = p.lane[half][0], p.lane[half][p.G - 1]
+                if first.q_len and first.row0 > 0:
+                    assert p.has_in and pi > 0
+                if last.q_len and last.row0 + p.R < last.q_len:
+                    assert p.has_out
+        for q, m in enumerate(lens):
+            assert covered[q] >= m and (m > 0 or covered[q] == 0)
+        padded = sum(2 * p.G * p.R for p in passes)
+        if len(lens) == 20:
+            assert padded < 1.04 * sum(lens)        # the 20-query benchmark set: under 4 % padded rows
+
+
+@pytest.mark.parametrize("lens", [[9, 30], [50, 20, 7], [70], [33, 34, 35, 36, 90]])
+def test_planned_passes_model_matches_oracle(built, lens, monkeypatch):
+    """The planner's passes, executed by the step-by-step model, reproduce the oracle (tiny R is
+    not compiled, so the model runs the real geometry on short sequences)."""
+    rng = np.random.default_rng(sum(lens))
+    mat = O.matrix("blosum62")
+    queries = [AA[rng.integers(0, 20, size=m)] for m in lens]
+    seqs = [AA[rng.integers(0, 20, size=rng.integers(1, 25))] for _ in range(3)]
+    seqs[1] = np.concatenate([queries[0][:20], seqs[1]])
+    passes = emu_u16.plan_passes(built, lens)
+    got = emu_u16.score_with_plan(passes, seqs, queries, mat, 10, 2)
+    want = np.array([[O.sw_score(q, s, mat, 10, 2) for s in seqs] for q in queries])
+    assert np.array_equal(got, want)
