@@ -53,7 +53,10 @@ typedef struct osw_hit {
 enum {
     OSW_K_U16 = 1,         /* packed 16-bit DPX inter-task kernel (first stage) */
     OSW_K_I32 = 2,         /* 32-bit kernel: re-score of flagged pairs; alone = score everything at 32 bit */
-    OSW_K_DEFAULT = 3
+    OSW_K_DEFAULT = 3,
+    /* how the two 16-bit halves of the first stage are used (default: chosen per query set) */
+    OSW_K_TWO_TRACK = 4,   /* always two query tracks against one database sequence */
+    OSW_K_PAIR_DB = 8      /* always one query track against two database sequences */
 };
 
 typedef struct osw_timing {

@@ -35,6 +35,7 @@ struct DevState {
     // database shard
     osw_shard shard = {};
     uint8_t *h_stream = nullptr;               // pinned copy of shard.stream (source of re-uploads)
+    uint8_t *h_pair = nullptr, *d_pair = nullptr;   // pair stream (pinned host copy, device)
     uint8_t *d_stream = nullptr; osw_chunk *d_chunks = nullptr; uint32_t *d_canon = nullptr;
     uint64_t *d_seq_off = nullptr; uint32_t *d_seq_len = nullptr;
     // per-search buffers (grown on demand)
@@ -78,6 +79,9 @@ int grow_pinned(T **ptr, size_t *cap, size_t need) {
 
 void free_db(DevState &d) {
     cudaSetDevice(d.dev);
+    cudaFree(d.d_pair); d.d_pair = nullptr;
+    if (d.h_pair) cudaFreeHost(d.h_pair);
+    d.h_pair = nullptr;
     cudaFree(d.d_stream); cudaFree(d.d_chunks); cudaFree(d.d_canon); cudaFree(d.d_seq_off); cudaFree(d.d_seq_len);
     cudaFree(d.d_bound[0]); cudaFree(d.d_bound[1]);
     d.d_stream = nullptr; d.d_chunks = nullptr; d.d_canon = nullptr; d.d_seq_off = nullptr; d.d_seq_len = nullptr;
@@ -91,6 +95,7 @@ int upload_db(DevState &d) {
     const osw_shard &s = d.shard;
     CK(cudaSetDevice(d.dev));
     CK(cudaMemcpyAsync(d.d_stream, d.h_stream, s.stream_bytes, cudaMemcpyHostToDevice, d.st));
+    CK(cudaMemcpyAsync(d.d_pair, d.h_pair, 2 * s.pair_cols, cudaMemcpyHostToDevice, d.st));
     CK(cudaMemcpyAsync(d.d_chunks, s.chunks, s.n_chunks * sizeof(osw_chunk), cudaMemcpyHostToDevice, d.st));
     CK(cudaMemcpyAsync(d.d_canon, s.canon, s.n_seqs * sizeof(uint32_t), cudaMemcpyHostToDevice, d.st));
     CK(cudaMemcpyAsync(d.d_seq_off, s.seq_off, s.n_seqs * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st));
@@ -226,7 +231,8 @@ extern "C" void osw_free(osw_ctx *c) {
 }
 
 extern "C" int osw_set_kernels(osw_ctx *c, int mask) {
-    if (!c || !(mask & (OSW_K_U16 | OSW_K_I32)) || !(mask & OSW_K_I32)) return OSW_E_ARG;   // the 32-bit stage is never optional
+    if (!c || !(mask & OSW_K_I32)) return OSW_E_ARG;   // the 32-bit stage is never optional
+    if ((mask & OSW_K_TWO_TRACK) && (mask & OSW_K_PAIR_DB)) return OSW_E_ARG;
     c->kernel_mask = mask;
     return OSW_OK;
 }
@@ -263,6 +269,10 @@ extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *
         CK(cudaMallocHost(&d.h_stream, s.stream_bytes ? s.stream_bytes : 1));
         memcpy(d.h_stream, s.stream, s.stream_bytes);
         free(d.shard.stream); d.shard.stream = nullptr;      // the pinned copy is the one kept
+        CK(cudaMalloc(&d.d_pair, s.pair_cols ? 2 * s.pair_cols : 1));
+        CK(cudaMallocHost(&d.h_pair, s.pair_cols ? 2 * s.pair_cols : 1));
+        memcpy(d.h_pair, s.pair_stream, 2 * s.pair_cols);
+        free(d.shard.pair_stream); d.shard.pair_stream = nullptr;
         int rc = upload_db(d);
         if (rc != OSW_OK) return rc;
         c->n_seqs_local += s.n_seqs; c->residues_local += s.n_residues; c->chunks_local += s.n_chunks;
@@ -283,7 +293,7 @@ extern "C" int osw_db_upload(osw_ctx *c, uint64_t *bytes) {
         int rc = upload_db(c->devs[i]);
         if (rc != OSW_OK) return rc;
         const osw_shard &s = c->devs[i].shard;
-        total += s.stream_bytes + s.n_chunks * sizeof(osw_chunk) + s.n_seqs * (sizeof(uint32_t) * 2 + sizeof(uint64_t));
+        total += s.stream_bytes + 2 * s.pair_cols + s.n_chunks * sizeof(osw_chunk) + s.n_seqs * (sizeof(uint32_t) * 2 + sizeof(uint64_t));
     }
     for (int i = 0; i < c->n_dev; ++i) {
         CK(cudaSetDevice(c->devs[i].dev));
@@ -370,8 +380,9 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
         bool need_bound = false;
         for (const OswPass &p : passes) need_bound |= p.has_in || p.has_out;
         if (need_bound && !d.d_bound[0]) {
-            CK(cudaMalloc(&d.d_bound[0], (s.stream_bytes ? s.stream_bytes : 1) * sizeof(uint2)));
-            CK(cudaMemsetAsync(d.d_bound[0], 0, (s.stream_bytes ? s.stream_bytes : 1) * sizeof(uint2), d.st));
+            const size_t cols = std::max<uint64_t>(std::max<uint64_t>(s.stream_bytes, s.pair_cols), 1);
+            CK(cudaMalloc(&d.d_bound[0], cols * sizeof(uint2)));
+            CK(cudaMemsetAsync(d.d_bound[0], 0, cols * sizeof(uint2), d.st));
         }
     }
 
@@ -392,7 +403,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
         for (const OswPass &ps : passes) {
             if (slot >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
             U16Params up;
-            up.stream = d.d_stream; up.chunks = d.d_chunks; up.n_chunks = s.n_chunks;
+            up.stream = d.d_stream; up.pair_stream = d.d_pair; up.chunks = d.d_chunks; up.n_chunks = s.n_chunks;
             up.queries = d.d_queries; up.q_off = d.d_qoff; up.matrix = d.d_matrix;
             up.scores = d.d_scores; up.n_seqs = N;
             up.bound = d.d_bound[0];
@@ -404,7 +415,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
                 return rc;
             }
             ++slot; ++*launches;
-            *padded_cells += (uint64_t)ps.G * ps.R * 2 * s.n_residues;
+            *padded_cells += (uint64_t)ps.G * ps.R * 2 * (ps.pair_db ? s.pair_cols : s.n_residues);
         }
         CK(cudaEventRecord(d.ev[1], d.st));
         *launches += osw_collect_flagged(d.d_scores, N, nq, d.d_pairs, d.d_counters, flag_cap, d.st);
@@ -433,7 +444,8 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
         std::vector<uint32_t> q_len((size_t)nq);
         for (int q = 0; q < nq; ++q) q_len[q] = q_off[q + 1] - q_off[q];
         passes.resize(MAX_PASSES);
-        const int n_pass = osw_plan_passes(q_len.data(), nq, passes.data(), MAX_PASSES);
+        const int mode = (c->kernel_mask & OSW_K_PAIR_DB) ? OSW_PLAN_PAIR_DB : (c->kernel_mask & OSW_K_TWO_TRACK) ? OSW_PLAN_TWO_TRACK : OSW_PLAN_AUTO;
+        const int n_pass = osw_plan_passes(q_len.data(), nq, passes.data(), MAX_PASSES, mode);
         if (n_pass < 0) { snprintf(g_err, sizeof g_err, "the queries need more than %d passes", MAX_PASSES); return OSW_E_ARG; }
         passes.resize((size_t)n_pass);
     }
@@ -513,9 +525,9 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
             // per-launch report: geometry, elapsed SM cycles, padded cell updates per SM-cycle
             for (uint32_t k = 0; k < slots[i] && k < passes.size(); ++k) {
                 const OswPass &ps = passes[k];
-                const double cells = 2.0 * ps.G * ps.R * (double)d.shard.n_residues;
-                fprintf(stderr, "osw trace: pass %u/%zu G=%d R=%d in=%d out=%d  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
-                        k + 1, passes.size(), ps.G, ps.R, ps.has_in, ps.has_out,
+                const double cells = 2.0 * ps.G * ps.R * (double)(ps.pair_db ? d.shard.pair_cols : d.shard.n_residues);
+                fprintf(stderr, "osw trace: pass %u/%zu G=%d R=%d in=%d out=%d pairdb=%d  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
+                        k + 1, passes.size(), ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db,
                         (unsigned long long)(d.h_cycles[k] / d.n_sms), cells / (double)d.h_cycles[k]);
             }
         }
@@ -553,7 +565,8 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
     tm.rescored_pairs = rescored;
     tm.launches = launches;
     tm.db_stream_bytes = 0;
-    for (int i = 0; i < c->n_dev; ++i) tm.db_stream_bytes += (uint64_t)slots[i] * c->devs[i].shard.stream_bytes;
+    for (int i = 0; i < c->n_dev; ++i)
+        for (const OswPass &ps : passes) tm.db_stream_bytes += ps.pair_db ? 2 * c->devs[i].shard.pair_cols : c->devs[i].shard.stream_bytes;
     if (timing) *timing = tm;
     return OSW_OK;
 }

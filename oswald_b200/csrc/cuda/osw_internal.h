@@ -47,13 +47,18 @@ struct OswPass {
     OswLaneDesc lane[2][32];   // [half][lane of group]
     int has_in;          // some half continues a query from the previous pass (bottom-row hand-over)
     int has_out;         // some half's last lane holds a query that continues in the next pass
+    int pair_db;         // pair-database mode: lane[1] == lane[0]; the halves score two database sequences
 };
 // Lays the queries out on two tracks and cuts the tracks into passes.  Returns the number of
 // passes (<= max_passes), or -1 if they do not fit.  Exported for the tests.
-extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes);
+#define OSW_PLAN_AUTO 0
+#define OSW_PLAN_TWO_TRACK 1
+#define OSW_PLAN_PAIR_DB 2
+extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes, int mode);
 
 struct U16Params {
     const uint8_t   *stream;
+    const uint8_t   *pair_stream; // two bytes per column (pair-database mode)
     const osw_chunk *chunks;     // descending-length order
     uint32_t         n_chunks;
     const uint8_t   *queries;    // all queries back to back (codes)
@@ -61,7 +66,7 @@ struct U16Params {
     const int8_t    *matrix;
     int32_t         *scores;     // [nq][n_seqs]
     uint64_t         n_seqs;
-    uint2           *bound;      // [stream_bytes] (H,F) bottom row handed from pass to pass, in place; or nullptr
+    uint2           *bound;      // [max(stream_bytes, pair_cols)] (H,F) bottom row handed from pass to pass, in place; or nullptr
     int              gap_open_extend, gap_extend;
     uint32_t        *chunk_counter;
     unsigned long long *cycle_acc;   // sum over CTAs of their elapsed clock64 cycles (one CTA per SM), or nullptr

@@ -55,7 +55,10 @@ int lanes_needed(const Track &tr, const uint32_t *q_len, size_t cur, uint32_t do
 
 }  // namespace
 
-extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes) {
+// Pair-database mode keeps two score tables in shared memory: with 32 lanes at most 28 rows each.
+static int pd_rmax(int G) { return G == 32 ? 28 : 40; }
+
+extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes, int mode) {
     if (!q_len || nq < 1 || !out || max_passes < 1) return -1;
     if (const char *e = getenv("OSW_RMAX")) {
         const int v = atoi(e);
@@ -72,6 +75,14 @@ extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int 
         t.q.push_back(q);
         t.rows += (q_len[q] + kRmax - 1) / kRmax * kRmax;
     }
+    // Two tracks need two comparable loads.  With a single query, or one much longer than the
+    // rest together, half of every word would idle: then all queries go on ONE track and the two
+    // halves score two different database sequences instead (pair-database mode).
+    const bool pair_db = mode == OSW_PLAN_PAIR_DB || (mode == OSW_PLAN_AUTO && tr[1].rows * 10 < tr[0].rows * 7);
+    if (pair_db) {
+        tr[0].q.clear(); tr[1].q.clear();
+        for (int q : order) if (q_len[q]) tr[0].q.push_back(q);
+    }
     size_t cur[2] = {0, 0};
     uint32_t done[2] = {0, 0};
     int n = 0;
@@ -79,11 +90,11 @@ extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int 
         if (cur[0] >= tr[0].q.size() && cur[1] >= tr[1].q.size()) break;
         if (n >= max_passes) return -1;
         // smallest geometry that finishes both tracks in this pass, if there is one
-        int G = 32, R = kRmax;
+        int G = 32, R = pair_db ? std::min(kRmax, pd_rmax(32)) : kRmax;
         uint64_t best = ~0ull;
         for (int gi = 0; gi < 4; ++gi)
             for (int ri = 0; ri < 8; ++ri) {
-                if (kR[ri] > kRmax) continue;
+                if (kR[ri] > kRmax || (pair_db && kR[ri] > pd_rmax(kG[gi]))) continue;
                 const int need = std::max(lanes_needed(tr[0], q_len, cur[0], done[0], kR[ri]),
                                           lanes_needed(tr[1], q_len, cur[1], done[1], kR[ri]));
                 if (need > kG[gi]) continue;
@@ -99,6 +110,8 @@ extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int 
         fill_half(tr[1], q_len, cur[1], done[1], G, R, p.lane[1], &in1, &out1);
         p.has_in = in0 || in1;
         p.has_out = out0 || out1;
+        p.pair_db = pair_db ? 1 : 0;
+        if (pair_db) memcpy(p.lane[1], p.lane[0], sizeof p.lane[0]);     // both halves: the same query rows
         ++n;
     }
     return n;

@@ -48,7 +48,7 @@ __host__ __device__ constexpr int pitch_quads(int R) { return (R / 4) | 1; }    
 __host__ __device__ constexpr int prof_quads(int G, int R) { return (G * pitch_quads(R) + 7) / 8 * 8; }
 __host__ __device__ constexpr int prof_copies(int G) { return G == 4 ? 2 : 1; }
 __host__ __device__ constexpr size_t prof_copy_bytes(int G, int R) { return (size_t)24 * prof_quads(G, R) * 16; }
-__host__ __device__ constexpr int block_threads(int R) { return R > 36 ? 384 : 512; }
+__host__ __device__ constexpr int block_threads(int R) { return R > 32 ? 384 : 512; }
 // A lane's R rows are swept as NUM_CHAINS independent segments (segment c works one column
 // behind segment c-1): two dependency chains per thread keep the DPX pipe fed.
 #ifndef OSW_NUM_CHAINS
@@ -67,6 +67,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 // profile reads: the profile is constant once built, so the compiler may schedule these freely
+__device__ __forceinline__ uint4 add4(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ uint4 lds128_const(uint32_t addr) {
     uint4 v;
     asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -77,13 +78,17 @@ struct KArgs {
     U16Params p;
     OswLaneDesc lane[2][32]; // [half][lane of group]: which query rows the lane holds
     uint32_t has_in, has_out;
+    uint32_t pair_db;        // PD mode (host-side dispatch only)
     uint32_t bias2;          // B | B<<16
     uint32_t nge2;           // (-ge) & 0xffff, both halves
     uint32_t ngoe_word;      // -(goe | goe<<16) as a 32-bit two's complement
     uint32_t bias;           // B
 };
 
-template <int G, int R, int THREADS>
+// PD = "pair database" mode: both halves work on the SAME query rows (track 0) against two
+// different database sequences zipped in the pair stream; the score word of a row is the sum of a
+// low-half table entry (first sequence's residue) and a high-half table entry (second one's).
+template <int G, int R, int THREADS, bool PD>
 __global__ void __launch_bounds__(THREADS, 1)
 sw_u16_kernel(const KArgs a) {
     constexpr int WARPS = THREADS / 32;
@@ -97,7 +102,8 @@ sw_u16_kernel(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     // layout: [profile copies][mailbox: WARPS*32 uint4][rings: WARPS*GROUPS*RING uint4]
     unsigned char *s_prof = smem;
-    constexpr int PROF_B = COPY_B * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0);
+    constexpr int TABLE_B = COPY_B * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0);
+    constexpr int PROF_B = TABLE_B * (PD ? 2 : 1);           // PD: low-half table, then high-half table
     uint4 *s_mail = reinterpret_cast<uint4 *>(smem + PROF_B);
     uint4 *s_ring = s_mail + WARPS * 32;
     __shared__ int s_mat[24 * 32];
@@ -125,12 +131,18 @@ sw_u16_kernel(const KArgs a) {
                 const uint32_t ra = da.row0 + 4 * k + r, rb = db.row0 + 4 * k + r;
                 const int ca = ra < da.q_len ? qa[ra] : OSW_PAD_CODE;
                 const int cb = rb < db.q_len ? qb[rb] : OSW_PAD_CODE;
-                w[r] = ((uint32_t)s_mat[ca * 32 + b] & 0xffffu) | ((uint32_t)s_mat[cb * 32 + b] << 16);
+                if (PD) w[r] = (uint32_t)s_mat[ca * 32 + b];            // track 0 only; split into halves below
+                else w[r] = ((uint32_t)s_mat[ca * 32 + b] & 0xffffu) | ((uint32_t)s_mat[cb * 32 + b] << 16);
             }
         }
         // the second copy (G == 4) sits 64 bytes further modulo 128, i.e. 4 bank groups away
         unsigned char *dst = s_prof + copy * (COPY_B + 64) + b * PITCH_B + slot * 16;
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (PD) {
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0] & 0xffffu, w[1] & 0xffffu, w[2] & 0xffffu, w[3] & 0xffffu);
+            *reinterpret_cast<uint4 *>(dst + TABLE_B) = make_uint4(w[0] << 16, w[1] << 16, w[2] << 16, w[3] << 16);
+        } else {
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
     __syncthreads();
 
@@ -140,6 +152,7 @@ sw_u16_kernel(const KArgs a) {
     const uint32_t mail_up = mail_self - 16;     // lane-1's mailbox (unused when t == 0)
     const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(s_ring + (wib * GROUPS + grp) * RING);
     const uint32_t B2 = a.bias2, NGE = a.nge2, GOE2 = 0u - a.ngoe_word;
+    constexpr uint32_t PAD_MSG = OSW_COL_PADBYTE | (OSW_COL_PADBYTE << 8);    // "no column": padding residue(s), no flags
     const bool multi_in = a.has_in != 0, has_out = a.has_out != 0;
     // what this lane is, per half: first lane of a query (its input from above is replaced by
     // "no row"), last lane of a query in this pass (it publishes that query's maximum)
@@ -158,26 +171,32 @@ sw_u16_kernel(const KArgs a) {
         const uint32_t ci = cbase + grp;
         const bool have = ci < p.n_chunks;
         osw_chunk ck;
-        if (have) ck = p.chunks[ci]; else { ck.stream_off = 0; ck.n_cols = 0; ck.n_seqs = 0; ck.seq0 = 0; ck.canon0 = 0; }
-        uint32_t steps = have ? ck.n_cols + NC * G - 1 : 0;
+        if (have) ck = p.chunks[ci];
+        else { ck.stream_off = 0; ck.n_cols = 0; ck.n_seqs = 0; ck.seq0 = 0; ck.canon0 = 0; ck.pair_off = 0; ck.n_pair_cols = 0; }
+        const uint32_t n_cols = PD ? ck.n_pair_cols : ck.n_cols;
+        const uint64_t col0 = PD ? ck.pair_off : ck.stream_off;       // first column in the (pair) stream
+        uint32_t steps = have ? n_cols + NC * G - 1 : 0;
 #pragma unroll
         for (int o = 16; o; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
         const uint32_t n_blocks = (steps + 31) / 32;
-        const uint8_t *col_src = p.stream + ck.stream_off + t * EPL;
-        const uint2 *bnd_src = multi_in ? p.bound + ck.stream_off + t * EPL : nullptr;
-        const uint32_t cols_padded = have ? (ck.n_cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN : 0;
+        const uint8_t *col_src = PD ? p.pair_stream + 2 * (col0 + t * EPL) : p.stream + col0 + t * EPL;
+        const uint2 *bnd_src = multi_in ? p.bound + col0 + t * EPL : nullptr;
+        constexpr uint32_t COL_ALIGN = PD ? 64 : OSW_CHUNK_ALIGN;
+        const uint32_t cols_padded = have ? (n_cols + COL_ALIGN - 1) / COL_ALIGN * COL_ALIGN : 0;
 
         // ring fill helpers: block b covers columns [32b, 32b+32); this lane fills EPL of them
-        uint32_t pre_cols[2];            // up to 8 stream bytes
+        uint32_t pre_cols[4];            // up to 8 stream bytes (16 in pair mode: two bytes per column)
         uint2 pre_bnd;                   // (G == 32 only: EPL == 1)
         auto prefetch = [&](uint32_t b) {
-            pre_cols[0] = pre_cols[1] = 0x17171717u;     // pad residues
+            pre_cols[0] = pre_cols[1] = pre_cols[2] = pre_cols[3] = 0x17171717u;     // pad residues
             pre_bnd = make_uint2(B2, B2);
             if (32 * b < cols_padded) {
-                const uint8_t *src = col_src + 32 * b;
-                if (EPL == 8) { uint2 v = __ldg(reinterpret_cast<const uint2 *>(src)); pre_cols[0] = v.x; pre_cols[1] = v.y; }
-                else if (EPL == 4) pre_cols[0] = __ldg(reinterpret_cast<const uint32_t *>(src));
-                else if (EPL == 2) pre_cols[0] = __ldg(reinterpret_cast<const uint16_t *>(src));
+                constexpr int BYTES = EPL * (PD ? 2 : 1);
+                const uint8_t *src = col_src + 32 * b * (PD ? 2 : 1);
+                if (BYTES == 16) { uint4 v = __ldg(reinterpret_cast<const uint4 *>(src)); pre_cols[0] = v.x; pre_cols[1] = v.y; pre_cols[2] = v.z; pre_cols[3] = v.w; }
+                else if (BYTES == 8) { uint2 v = __ldg(reinterpret_cast<const uint2 *>(src)); pre_cols[0] = v.x; pre_cols[1] = v.y; }
+                else if (BYTES == 4) pre_cols[0] = __ldg(reinterpret_cast<const uint32_t *>(src));
+                else if (BYTES == 2) pre_cols[0] = __ldg(reinterpret_cast<const uint16_t *>(src));
                 else pre_cols[0] = __ldg(src);
                 if (EPL == 1 && multi_in) pre_bnd = __ldcg(bnd_src + 32 * b);
             }
@@ -186,8 +205,10 @@ sw_u16_kernel(const KArgs a) {
             const uint32_t dst = ring_base + ((b & 1) * 32 + t * EPL) * 16;
 #pragma unroll
             for (int e = 0; e < EPL; ++e) {
-                const uint32_t byte = (pre_cols[e >> 2] >> (8 * (e & 3))) & 0xffu;
-                sts128(dst + e * 16, make_uint4(pre_bnd.x, pre_bnd.y, B2, byte));
+                // message word 3: residue + flags in bits 0-7 (pair mode: second residue in bits 8-15)
+                const uint32_t w = PD ? (pre_cols[e >> 1] >> (16 * (e & 1))) & 0xffffu
+                                      : (pre_cols[e >> 2] >> (8 * (e & 3))) & 0xffu;
+                sts128(dst + e * 16, make_uint4(pre_bnd.x, pre_bnd.y, B2, w));
             }
         };
         prefetch(0);
@@ -199,11 +220,11 @@ sw_u16_kernel(const KArgs a) {
         uint32_t diag[NC], run = B2;
         uint4 mid[NC];                   // mid[c]: message segment c-1 produced in the previous step
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { diag[c] = B2; mid[c] = make_uint4(B2, B2, B2, OSW_COL_PADBYTE); }
+        for (int c = 0; c < NC; ++c) { diag[c] = B2; mid[c] = make_uint4(B2, B2, B2, PAD_MSG); }
         uint32_t seq = ck.seq0;
-        uint2 *out_base = has_out ? p.bound + ck.stream_off : nullptr;
+        uint2 *out_base = has_out ? p.bound + col0 : nullptr;
         const uint32_t out_limit = t == G - 1 ? cols_padded : 0u;      // only the group's last lane stores
-        sts128(mail_self, make_uint4(B2, B2, B2, OSW_COL_PADBYTE));
+        sts128(mail_self, make_uint4(B2, B2, B2, PAD_MSG));
         __syncwarp();
 
         for (uint32_t blk = 0; blk < n_blocks; ++blk) {
@@ -221,7 +242,7 @@ sw_u16_kernel(const KArgs a) {
 #endif
 #pragma unroll
                 for (int c = 1; c < NC; ++c) msg[c] = mid[c];
-                uint32_t paddr[NC];
+                uint32_t paddr[NC], paddr_hi[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     if (msg[c].w & OSW_COL_FIRST) {
@@ -230,6 +251,7 @@ sw_u16_kernel(const KArgs a) {
                         diag[c] = B2;
                     }
                     paddr[c] = prof_lane + (msg[c].w & OSW_COL_CODE) * PITCH_B + seg_begin(R, NC, c) * 16;
+                    paddr_hi[c] = PD ? prof_lane + TABLE_B + ((msg[c].w >> 8) & OSW_COL_CODE) * PITCH_B + seg_begin(R, NC, c) * 16 : 0u;
                 }
                 // Row sweeps of the NC segments, interleaved: they are independent dependency
                 // chains.  t (the diagonal term) of row r+1 is issued before H of row r is written,
@@ -240,6 +262,7 @@ sw_u16_kernel(const KArgs a) {
                 for (int c = 0; c < NC; ++c) {
                     F[c] = msg[c].y; cm[c] = msg[c].z; Heven[c] = B2;
                     sv[c] = lds128_const(paddr[c]);
+                    if (PD) sv[c] = add4(sv[c], lds128_const(paddr_hi[c]));
                     t_next[c] = __viaddmax_u16x2(diag[c], sv[c].x, E[4 * seg_begin(R, NC, c)]);
                 }
 #pragma unroll
@@ -248,7 +271,10 @@ sw_u16_kernel(const KArgs a) {
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         sn[c] = sv[c];
-                        if (kk + 1 < seg_begin(R, NC, c + 1) - seg_begin(R, NC, c)) sn[c] = lds128_const(paddr[c] + (kk + 1) * 16);
+                        if (kk + 1 < seg_begin(R, NC, c + 1) - seg_begin(R, NC, c)) {
+                            sn[c] = lds128_const(paddr[c] + (kk + 1) * 16);
+                            if (PD) sn[c] = add4(sn[c], lds128_const(paddr_hi[c] + (kk + 1) * 16));
+                        }
                     }
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
@@ -288,8 +314,15 @@ sw_u16_kernel(const KArgs a) {
                     const uint32_t lo = run & 0xffffu, hi = run >> 16;
                     const int sa = lo >= FLAG_THRESHOLD ? OSW_SCORE_FLAGGED : (int)(lo - a.bias);
                     const int sb = hi >= FLAG_THRESHOLD ? OSW_SCORE_FLAGGED : (int)(hi - a.bias);
-                    if (emit & 1u) atomicMax(p.scores + (size_t)a.lane[0][t].query * p.n_seqs + seq, sa);
-                    if (emit & 2u) atomicMax(p.scores + (size_t)a.lane[1][t].query * p.n_seqs + seq, sb);
+                    if (PD) {       // low half: sequence 2p of the chunk, high half: sequence 2p+1 (if there is one)
+                        int32_t *row = p.scores + (size_t)a.lane[0][t].query * p.n_seqs;
+                        atomicMax(row + seq, sa);
+                        if (seq + 1 < ck.seq0 + ck.n_seqs) atomicMax(row + seq + 1, sb);
+                        ++seq;               // a pair is two sequences (second increment below)
+                    } else {
+                        if (emit & 1u) atomicMax(p.scores + (size_t)a.lane[0][t].query * p.n_seqs + seq, sa);
+                        if (emit & 2u) atomicMax(p.scores + (size_t)a.lane[1][t].query * p.n_seqs + seq, sb);
+                    }
                     ++seq;
                     run = B2;
                 }
@@ -304,31 +337,29 @@ sw_u16_kernel(const KArgs a) {
     if (p.cycle_acc && threadIdx.x == 0) atomicAdd(p.cycle_acc, (unsigned long long)(clock64() - clk0));
 }
 
-template <int G, int R, int THREADS>
+template <int G, int R, int THREADS, bool PD>
 int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
-    const size_t prof = prof_copy_bytes(G, R) * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0);
+    const size_t prof = (prof_copy_bytes(G, R) * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0)) * (PD ? 2 : 1);
     const size_t smem = prof + (size_t)(THREADS / 32) * 32 * 16 + (size_t)(THREADS / 32) * (32 / G) * RING * 16;
     static bool configured[64] = {};          // the attribute is per device
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return OSW_E_CUDA;
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        if (cudaFuncSetAttribute(sw_u16_kernel<G, R, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (smem > 227 * 1024) return OSW_E_ARG;
+        if (cudaFuncSetAttribute(sw_u16_kernel<G, R, THREADS, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return OSW_E_CUDA;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    sw_u16_kernel<G, R, THREADS><<<n_sms, THREADS, smem, st>>>(a);
+    sw_u16_kernel<G, R, THREADS, PD><<<n_sms, THREADS, smem, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? OSW_OK : OSW_E_CUDA;
 }
 
-// CTA size: 512 threads (128 registers each) up to R = 36, 384 (168 registers) above.
-// OSW_THREADS=256|384 overrides for experiments.
+// CTA size: 512 threads (128 registers each) up to R = 32, 384 (168 registers) above.
 template <int G, int R>
 int launch_one(const KArgs &a, int n_sms, cudaStream_t st) {
-    static int forced = -1;
-    if (forced < 0) { const char *e = getenv("OSW_THREADS"); forced = e ? atoi(e) : 0; }
-    if (forced == 256) return launch_threads<G, R, 256>(a, n_sms, st);
-    if (forced == 384 || R > 36) return launch_threads<G, R, 384>(a, n_sms, st);
-    return launch_threads<G, R, 512>(a, n_sms, st);
+    constexpr int THREADS = block_threads(R);
+    if (a.pair_db) return launch_threads<G, R, THREADS, true>(a, n_sms, st);
+    return launch_threads<G, R, THREADS, false>(a, n_sms, st);
 }
 
 template <int G>
@@ -354,6 +385,7 @@ int osw_launch_u16(const U16Params &p, const OswPass &pass, int n_sms, cudaStrea
     memcpy(a.lane, pass.lane, sizeof a.lane);
     a.has_in = pass.has_in && p.bound ? 1u : 0u;
     a.has_out = pass.has_out && p.bound ? 1u : 0u;
+    a.pair_db = pass.pair_db ? 1u : 0u;
     if ((pass.has_in || pass.has_out) && !p.bound) return OSW_E_ARG;
     const uint32_t goe = (uint32_t)p.gap_open_extend, ge = (uint32_t)p.gap_extend;
     const uint32_t B = goe + ge + 32u;

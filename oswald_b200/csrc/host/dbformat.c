@@ -25,19 +25,31 @@ uint64_t osw_count_chunks(const uint64_t *offsets, uint64_t n_seqs, uint32_t chu
     return walk_chunks(offsets, n_seqs, chunk_cols, NULL, NULL);
 }
 
-typedef struct { uint32_t shard, n_shards; uint64_t seqs, cols, bytes, chunks; uint32_t max_len;
+#define OSW_PAIR_ALIGN 64      /* columns */
+typedef struct { uint32_t shard, n_shards; uint64_t seqs, cols, bytes, chunks, pair_cols; uint32_t max_len;
                  const uint64_t *off; } tally_t;
+/* columns of a chunk in the pair stream: sum over pairs of the longer length (ascending order:
+ * the second sequence of a pair, or the single last one) */
+static uint64_t pair_columns(const uint64_t *off, uint64_t first, uint64_t ns) {
+    uint64_t cols = 0;
+    for (uint64_t k = 0; k < ns; k += 2) {
+        uint64_t i = first + (k + 1 < ns ? k + 1 : k);
+        cols += off[i + 1] - off[i];
+    }
+    return cols;
+}
 static void tally_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t cols) {
     tally_t *t = (tally_t *)u;
     if (c % t->n_shards != t->shard) return;
     t->seqs += ns; t->cols += cols; t->chunks++;
     t->bytes += (cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
+    t->pair_cols += (pair_columns(t->off, first, ns) + OSW_PAIR_ALIGN - 1) / OSW_PAIR_ALIGN * OSW_PAIR_ALIGN;
     uint64_t last = t->off[first + ns] - t->off[first + ns - 1];   /* longest: order is ascending */
     if (last > t->max_len) t->max_len = (uint32_t)last;
 }
 
 typedef struct { uint32_t shard, n_shards; const uint8_t *res; const uint64_t *off; osw_shard *s;
-                 uint64_t seq_cursor, byte_cursor; uint32_t chunk_cursor; } fill_t;
+                 uint64_t seq_cursor, byte_cursor, pair_cursor; uint32_t chunk_cursor; } fill_t;
 static void fill_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t cols) {
     fill_t *f = (fill_t *)u;
     if (c % f->n_shards != f->shard) return;
@@ -59,6 +71,27 @@ static void fill_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t c
     uint64_t padded = (cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
     memset(p, OSW_COL_PADBYTE, padded - cols);
     f->byte_cursor += padded;
+    /* pair stream of the same chunk */
+    ck->pair_off = f->pair_cursor; ck->reserved = 0;
+    uint8_t *q = s->pair_stream + 2 * f->pair_cursor;
+    uint64_t pc = 0;
+    for (uint64_t k = 0; k < ns; k += 2) {
+        const uint64_t ia = first + k, ib = first + k + 1;
+        const int has_b = k + 1 < ns;
+        const uint64_t la = f->off[ia + 1] - f->off[ia], lb = has_b ? f->off[ib + 1] - f->off[ib] : 0;
+        const uint64_t n = la > lb ? la : lb;
+        const uint8_t *a = f->res + f->off[ia], *b = has_b ? f->res + f->off[ib] : NULL;
+        for (uint64_t j = 0; j < n; ++j) {
+            q[2 * j] = (uint8_t)(j < la ? (a[j] & OSW_COL_CODE) : OSW_COL_PADBYTE);
+            q[2 * j + 1] = (uint8_t)(j < lb ? (b[j] & OSW_COL_CODE) : OSW_COL_PADBYTE);
+        }
+        if (n) { q[0] |= OSW_COL_FIRST; q[2 * (n - 1)] |= OSW_COL_LAST; }
+        q += 2 * n; pc += n;
+    }
+    ck->n_pair_cols = (uint32_t)pc;
+    const uint64_t pc_padded = (pc + OSW_PAIR_ALIGN - 1) / OSW_PAIR_ALIGN * OSW_PAIR_ALIGN;
+    memset(q, OSW_COL_PADBYTE, 2 * (pc_padded - pc));
+    f->pair_cursor += pc_padded;
 }
 
 int osw_shard_build(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
@@ -71,12 +104,14 @@ int osw_shard_build(const uint8_t *residues, const uint64_t *offsets, uint64_t n
     walk_chunks(offsets, n_seqs, chunk_cols, tally_cb, &t);
     out->n_seqs = t.seqs; out->n_residues = t.cols; out->stream_bytes = t.bytes;
     out->n_chunks = (uint32_t)t.chunks; out->max_len = t.max_len;
+    out->pair_cols = t.pair_cols;
     out->stream  = (uint8_t *)malloc(t.bytes ? t.bytes : 1);
+    out->pair_stream = (uint8_t *)malloc(t.pair_cols ? 2 * t.pair_cols : 1);
     out->chunks  = (osw_chunk *)malloc((t.chunks ? t.chunks : 1) * sizeof(osw_chunk));
     out->canon   = (uint32_t *)malloc((t.seqs ? t.seqs : 1) * sizeof(uint32_t));
     out->seq_off = (uint64_t *)malloc((t.seqs ? t.seqs : 1) * sizeof(uint64_t));
     out->seq_len = (uint32_t *)malloc((t.seqs ? t.seqs : 1) * sizeof(uint32_t));
-    if (!out->stream || !out->chunks || !out->canon || !out->seq_off || !out->seq_len) {
+    if (!out->stream || !out->pair_stream || !out->chunks || !out->canon || !out->seq_off || !out->seq_len) {
         osw_shard_free(out); return -1;
     }
     fill_t f; memset(&f, 0, sizeof f);
@@ -87,6 +122,6 @@ int osw_shard_build(const uint8_t *residues, const uint64_t *offsets, uint64_t n
 
 void osw_shard_free(osw_shard *s) {
     if (!s) return;
-    free(s->stream); free(s->chunks); free(s->canon); free(s->seq_off); free(s->seq_len);
+    free(s->stream); free(s->pair_stream); free(s->chunks); free(s->canon); free(s->seq_off); free(s->seq_len);
     memset(s, 0, sizeof *s);
 }

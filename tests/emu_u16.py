@@ -128,25 +128,65 @@ class LaneDesc(C.Structure):
 
 
 class Pass(C.Structure):
-    _fields_ = [("G", C.c_int), ("R", C.c_int), ("lane", (LaneDesc * 32) * 2), ("has_in", C.c_int), ("has_out", C.c_int)]
+    _fields_ = [("G", C.c_int), ("R", C.c_int), ("lane", (LaneDesc * 32) * 2), ("has_in", C.c_int), ("has_out", C.c_int),
+                ("pair_db", C.c_int)]
 
 
-def plan_passes(lib, q_lens, max_passes=256):
-    lib.osw_plan_passes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+PLAN_AUTO, PLAN_TWO_TRACK, PLAN_PAIR_DB = 0, 1, 2
+
+
+def plan_passes(lib, q_lens, max_passes=256, mode=PLAN_TWO_TRACK):
+    lib.osw_plan_passes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
     lib.osw_plan_passes.restype = C.c_int
     arr = (C.c_uint32 * len(q_lens))(*q_lens)
     out = (Pass * max_passes)()
-    n = lib.osw_plan_passes(arr, len(q_lens), out, max_passes)
+    n = lib.osw_plan_passes(arr, len(q_lens), out, max_passes, mode)
     assert n >= 0
     return [out[i] for i in range(n)]
 
 
+def build_pair_streams(seqs):
+    """Pair-database mode (dbformat.c): sequences 2p and 2p+1 zipped, the shorter padded; returns
+    the two per-half column streams (flags of the pair's columns on both) and the pair count."""
+    a_cols, b_cols = [], []
+    for p in range(0, len(seqs), 2):
+        a = [int(c) & 31 for c in seqs[p]]
+        b = [int(c) & 31 for c in seqs[p + 1]] if p + 1 < len(seqs) else []
+        n = max(len(a), len(b))
+        a += [PAD] * (n - len(a))
+        b += [PAD] * (n - len(b))
+        if n:
+            a[0] |= FIRST; b[0] |= FIRST
+            a[-1] |= LAST; b[-1] |= LAST
+        a_cols += a
+        b_cols += b
+    return a_cols, b_cols, (len(seqs) + 1) // 2
+
+
 def score_with_plan(passes, seqs, queries, mat, go, ge, chains=2):
     """All queries against one chunk, following the planner's passes for both halves."""
-    stream = build_stream(seqs)
     n_seqs = sum(1 for s in seqs if len(s))
+    if passes and passes[0].pair_db:
+        assert n_seqs == len(seqs)
+        sa, sb, n_pairs = build_pair_streams(seqs)
+        out = np.zeros((len(queries), n_seqs), dtype=np.int64)
+        for half, stream in ((0, sa), (1, sb)):
+            scores = {q: [0] * n_pairs for q in range(len(queries))}
+            _run_half(passes, half, stream, n_pairs, queries, mat, go, ge, chains, scores)
+            for q in range(len(queries)):
+                for p in range(n_pairs):
+                    if 2 * p + half < n_seqs:
+                        out[q, 2 * p + half] = scores[q][p]
+        return out
+    stream = build_stream(seqs)
     scores = {q: [0] * n_seqs for q in range(len(queries))}
     for half in (0, 1):
+        _run_half(passes, half, stream, n_seqs, queries, mat, go, ge, chains, scores)
+    return np.array([scores[q] for q in range(len(queries))], dtype=np.int64)
+
+
+def _run_half(passes, half, stream, n_seqs, queries, mat, go, ge, chains, scores):
+    if True:
         bound = None
         for p in passes:
             seg = segment_rows(p.R, chains)
@@ -161,4 +201,3 @@ def score_with_plan(passes, seqs, queries, mat, go, ge, chains=2):
                                      "emit": d.query if (d.flags & LANE_EMIT) and d.q_len and c == len(seg) - 1 else None})
                     first += n_rows
             bound = run_pass(stream, n_seqs, stations, mat, go, ge, bound if p.has_in else None, bool(p.has_out), scores)
-    return np.array([scores[q] for q in range(len(queries))], dtype=np.int64)

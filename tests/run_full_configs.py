@@ -188,7 +188,7 @@ def run_config(cfg, s, args, rng, queries_all):
         r["titin_length_sequences"] = len(extra)
         what = "Swiss-Prot-sized DB + 16 sequences of 35k-65k residues (one with 6 tandem copies of the 5478 query), BLOSUM62"
     r.update({"config": cfg, "what": what, "sequences": db.n_seqs, "residues": db.n_residues, "gcups_device": gcups,
-              "device_ms": tm["device_ms"], "launches": tm["launches"], "rescored_pairs_last_run": tm["rescored_pairs"],
+              "device_ms": tm["device_ms"], "score_ms": tm["score_ms"], "topr_ms": tm["topr_ms"], "launches": tm["launches"], "rescored_pairs_last_run": tm["rescored_pairs"],
               "wall_seconds_total": round(time.time() - t_start, 1)})
     return r
 

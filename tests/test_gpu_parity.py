@@ -46,7 +46,8 @@ def check(searcher, db, q, name, go, ge, top, mask=capi.OSW_K_DEFAULT, want=None
     return tm
 
 
-@pytest.mark.parametrize("mask", [capi.OSW_K_I32, capi.OSW_K_DEFAULT])
+@pytest.mark.parametrize("mask", [capi.OSW_K_I32, capi.OSW_K_DEFAULT, capi.OSW_K_DEFAULT | capi.OSW_K_TWO_TRACK,
+                                  capi.OSW_K_DEFAULT | capi.OSW_K_PAIR_DB])
 @pytest.mark.parametrize("name", CASES)
 def test_golden_cases(searcher, name, mask):
     """Score matrices and printed top-r lists of the reference's host AVX2 path."""
@@ -62,16 +63,22 @@ def test_golden_cases(searcher, name, mask):
         for qi, h in enumerate(run["hits"]):
             got = [[s, db.titles[i]] for s, i in hits[qi]]
             assert got == h["top"], (name, run["matrix"], qi)
-        if mask == capi.OSW_K_DEFAULT:
+        if mask != capi.OSW_K_I32:
             # the reference needed its 16- and 32-bit stages here (scores up to 44 783 > 32 767);
             # the biased unsigned 16-bit kernel holds them, so nothing is re-scored
             assert tm["rescored_pairs"] == 0
 
 
+MODES = {"auto": capi.OSW_K_DEFAULT, "two_track": capi.OSW_K_DEFAULT | capi.OSW_K_TWO_TRACK,
+         "pair_db": capi.OSW_K_DEFAULT | capi.OSW_K_PAIR_DB}
+
+
+@pytest.mark.parametrize("mode", ["auto", "two_track", "pair_db"])
 @pytest.mark.parametrize("lengths", [[144], [5, 37, 144, 189], [1, 1, 2], [144, 189, 222, 375, 464, 567, 657],
                                       [1000, 1500], [2005], [1537, 3005]])
-def test_random_db_all_query_geometries(searcher, lengths):
-    """Every (G, R, passes) plan the query lengths select, odd and even query counts."""
+def test_random_db_all_query_geometries(searcher, lengths, mode):
+    """Every (G, R, passes) plan the query lengths select, odd and even query counts, with the two
+    halves of the packed words used as two query tracks or as two database sequences."""
     rng = np.random.default_rng(sum(lengths))
     seqs = rand_seqs(rng, 700, 1, 500)
     q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in lengths])
@@ -79,7 +86,7 @@ def test_random_db_all_query_geometries(searcher, lengths):
     seqs[5] = np.concatenate([q.query(0), rng.permutation(q.query(q.n - 1))])
     db = make_db(seqs)
     searcher.load_db(db)
-    check(searcher, db, q, "blosum62", 10, 2, 10)
+    check(searcher, db, q, "blosum62", 10, 2, 10, mask=MODES[mode])
 
 
 @pytest.mark.parametrize("name,go,ge", [("blosum45", 14, 2), ("blosum50", 10, 2), ("blosum80", 10, 2), ("blosum90", 10, 2),
@@ -133,7 +140,8 @@ def test_long_sequences_and_chunk_boundaries(searcher):
     want = oracle_scores(q, db, "blosum62", 10, 2)
     for k in (0, 64, 300):
         searcher.load_db(db, max_chunk_residues=k)
-        check(searcher, db, q, "blosum62", 10, 2, 10, want=want)
+        for mode in MODES.values():
+            check(searcher, db, q, "blosum62", 10, 2, 10, mask=mode, want=want)
 
 
 def test_overflow_rescore_exact(searcher):
@@ -153,8 +161,9 @@ def test_overflow_rescore_exact(searcher):
     searcher.load_db(db)
     want = oracle_scores(q, db, "pam30", 9, 1)
     assert want.max() > 2 * 65535 and ((want > 64000) & (want < 65400)).any()
-    tm = check(searcher, db, q, "pam30", 9, 1, 10, want=want)
-    assert tm["rescored_pairs"] == int((want + 9 + 1 + 1 + 32 >= 65504).sum())      # bias = go + 2*ge + 32
+    for mode in MODES.values():
+        tm = check(searcher, db, q, "pam30", 9, 1, 10, mask=mode, want=want)
+        assert tm["rescored_pairs"] == int((want + 9 + 1 + 1 + 32 >= 65504).sum())      # bias = go + 2*ge + 32
 
 
 def test_sharded_contexts_merge_to_the_same_hits(built):

@@ -38,12 +38,14 @@ def test_no_device_is_an_error_not_a_fallback(built):
 
 class Chunk(C.Structure):
     _fields_ = [("stream_off", C.c_uint64), ("n_cols", C.c_uint32), ("n_seqs", C.c_uint32),
-                ("seq0", C.c_uint32), ("canon0", C.c_uint32)]
+                ("seq0", C.c_uint32), ("canon0", C.c_uint32), ("pair_off", C.c_uint64),
+                ("n_pair_cols", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Shard(C.Structure):
     _fields_ = [("n_seqs", C.c_uint64), ("n_residues", C.c_uint64), ("stream_bytes", C.c_uint64),
                 ("n_chunks", C.c_uint32), ("max_len", C.c_uint32), ("stream", C.POINTER(C.c_uint8)),
+                ("pair_cols", C.c_uint64), ("pair_stream", C.POINTER(C.c_uint8)),
                 ("chunks", C.POINTER(Chunk)), ("canon", C.POINTER(C.c_uint32)),
                 ("seq_off", C.POINTER(C.c_uint64)), ("seq_len", C.POINTER(C.c_uint32))]
 
@@ -73,7 +75,8 @@ def test_chunk_streams(built, n_shards):
     for sh in range(n_shards):
         s = build_shard(built, db, sh, n_shards, 1024)
         stream = np.ctypeslib.as_array(s.stream, shape=(s.stream_bytes,))
-        assert s.stream_bytes % 128 == 0
+        pair = np.ctypeslib.as_array(s.pair_stream, shape=(2 * s.pair_cols,))
+        assert s.stream_bytes % 128 == 0 and s.pair_cols % 64 == 0
         residues.append(s.n_residues)
         prev_len = None
         for c in range(s.n_chunks):
@@ -102,6 +105,15 @@ def test_chunk_streams(built, n_shards):
             assert pos - ck.stream_off == ck.n_cols
             pad_end = ck.stream_off + (ck.n_cols + 127) // 128 * 128
             assert np.all(stream[pos:pad_end] == 23)
+            # the pair stream of the chunk: sequences 2p, 2p+1 zipped, two bytes per column
+            seqs = [db.sequence(ck.canon0 + k) for k in range(ck.n_seqs)]
+            sa, sb, n_pairs = emu_u16.build_pair_streams(seqs)
+            assert ck.pair_off % 64 == 0 and ck.n_pair_cols == len(sa)
+            got = pair[2 * ck.pair_off:2 * (ck.pair_off + ck.n_pair_cols)].reshape(-1, 2)
+            assert np.array_equal(got[:, 0], np.array(sa, dtype=np.uint8))
+            assert np.array_equal(got[:, 1], np.array(sb, dtype=np.uint8) & 31)
+            pad_cols = (ck.n_pair_cols + 63) // 64 * 64
+            assert np.all(pair[2 * (ck.pair_off + ck.n_pair_cols):2 * (ck.pair_off + pad_cols)] == 23)
         built.osw_shard_free(C.byref(s))
     assert np.all(seen == 1)                           # every sequence in exactly one shard
     if n_shards > 1:
@@ -233,6 +245,34 @@ def test_pass_planner_layout(built):
         padded = sum(2 * p.G * p.R for p in passes)
         if len(lens) == 20:
             assert padded < 1.04 * sum(lens)        # the 20-query benchmark set: under 4 % padded rows
+
+
+def test_pair_db_plan(built):
+    """Pair-database plans: one track, both halves identical, chosen automatically for a single
+    query or a lopsided query set; never more than 28 rows per lane with 32 lanes (two tables)."""
+    for lens, expect in (([144], True), ([5478], True), ([5000, 100, 100], True), ([144, 189], False),
+                         ([144, 189, 222, 375, 464, 567, 657, 727, 850, 1000], False)):
+        passes = emu_u16.plan_passes(built, lens, 4096, emu_u16.PLAN_AUTO)
+        assert bool(passes[0].pair_db) == expect, lens
+        for p in passes:
+            assert bool(p.pair_db) == expect
+            if p.pair_db:
+                assert p.G != 32 or p.R <= 28
+                for t in range(p.G):
+                    a, b = p.lane[0][t], p.lane[1][t]
+                    assert (a.query, a.q_len, a.row0, a.flags) == (b.query, b.q_len, b.row0, b.flags)
+
+
+@pytest.mark.parametrize("lens", [[40], [70, 9]])
+def test_pair_db_model_matches_oracle(built, lens):
+    rng = np.random.default_rng(sum(lens) + 1)
+    mat = O.matrix("pam30")
+    queries = [AA[rng.integers(0, 20, size=m)] for m in lens]
+    seqs = sorted([AA[rng.integers(0, 20, size=rng.integers(1, 25))] for _ in range(5)], key=len)
+    passes = emu_u16.plan_passes(built, lens, 64, emu_u16.PLAN_PAIR_DB)
+    got = emu_u16.score_with_plan(passes, seqs, queries, mat, 9, 1)
+    want = np.array([[O.sw_score(q, s, mat, 9, 1) for s in seqs] for q in queries])
+    assert np.array_equal(got, want)
 
 
 @pytest.mark.parametrize("lens", [[9, 30], [50, 20, 7], [70], [33, 34, 35, 36, 90]])
