@@ -204,7 +204,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels", type=int, default=3, help="kernel mask (1|2 = default, 2 = 32-bit only)")
     ap.add_argument("--chunk-cols", type=int, default=0, help="residues per chunk (0 = library default)")
+    ap.add_argument("--query-lengths", default="", help="comma-separated subset/alternative query lengths (experiments; default: the 20 standard lengths)")
     args = ap.parse_args()
+    if args.query_lengths:
+        global QUERY_LENGTHS
+        QUERY_LENGTHS = [int(x) for x in args.query_lengths.split(",")]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -77,8 +77,10 @@ extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int 
     }
     // Two tracks need two comparable loads.  With a single query, or one much longer than the
     // rest together, half of every word would idle: then all queries go on ONE track and the two
-    // halves score two different database sequences instead (pair-database mode).
-    const bool pair_db = mode == OSW_PLAN_PAIR_DB || (mode == OSW_PLAN_AUTO && tr[1].rows * 10 < tr[0].rows * 7);
+    // halves score two different database sequences instead (pair-database mode).  That mode runs at
+    // about 78 % of the two-track rate per cell (two table reads per row), so it pays when the
+    // lighter track holds less than 56 % of the heavier one's rows.
+    const bool pair_db = mode == OSW_PLAN_PAIR_DB || (mode == OSW_PLAN_AUTO && tr[1].rows * 100 < tr[0].rows * 56);
     if (pair_db) {
         tr[0].q.clear(); tr[1].q.clear();
         for (int q : order) if (q_len[q]) tr[0].q.push_back(q);
@@ -86,11 +88,24 @@ extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int 
     size_t cur[2] = {0, 0};
     uint32_t done[2] = {0, 0};
     int n = 0;
+    // Several passes: as few as the tallest geometry allows, then the smallest R that still fits
+    // that many passes (1000 rows are two passes of 32 x 16, not 32 x 28 + 32 x 16).
+    const int r_cap = pair_db ? std::min(kRmax, pd_rmax(32)) : kRmax;
+    int r_full = r_cap;
+    {
+        const int need_cap = std::max(lanes_needed(tr[0], q_len, 0, 0, r_cap), lanes_needed(tr[1], q_len, 0, 0, r_cap));
+        const int n_min = (need_cap + 31) / 32;
+        for (int ri = 7; ri >= 0; --ri) {
+            if (kR[ri] > r_cap) continue;
+            const int need = std::max(lanes_needed(tr[0], q_len, 0, 0, kR[ri]), lanes_needed(tr[1], q_len, 0, 0, kR[ri]));
+            if ((need + 31) / 32 <= n_min) r_full = kR[ri];
+        }
+    }
     for (;;) {
         if (cur[0] >= tr[0].q.size() && cur[1] >= tr[1].q.size()) break;
         if (n >= max_passes) return -1;
         // smallest geometry that finishes both tracks in this pass, if there is one
-        int G = 32, R = pair_db ? std::min(kRmax, pd_rmax(32)) : kRmax;
+        int G = 32, R = r_full;
         uint64_t best = ~0ull;
         for (int gi = 0; gi < 4; ++gi)
             for (int ri = 0; ri < 8; ++ri) {

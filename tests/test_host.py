@@ -250,7 +250,7 @@ def test_pass_planner_layout(built):
 def test_pair_db_plan(built):
     """Pair-database plans: one track, both halves identical, chosen automatically for a single
     query or a lopsided query set; never more than 28 rows per lane with 32 lanes (two tables)."""
-    for lens, expect in (([144], True), ([5478], True), ([5000, 100, 100], True), ([144, 189], False),
+    for lens, expect in (([144], True), ([5478], True), ([5000, 100, 100], True), ([144, 189], False), ([2005, 1500], False), ([1000, 400], True),
                          ([144, 189, 222, 375, 464, 567, 657, 727, 850, 1000], False)):
         passes = emu_u16.plan_passes(built, lens, 4096, emu_u16.PLAN_AUTO)
         assert bool(passes[0].pair_db) == expect, lens
