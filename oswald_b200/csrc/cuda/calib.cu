@@ -60,6 +60,22 @@ __global__ void __launch_bounds__(CAL_THREADS) calib_kernel(CalArgs g) {
                 for (int r = 0; r < 16; ++r) sc[r] = Hl[(r + 5) & 15] ^ g.a;     // any per-row value already in a register
             }
             uint32_t Hprev = 0;
+            if (MODE == 9) {
+                // E kept clamped at >= B: then t >= B and H needs only a 2-input max
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    uint32_t t = __viaddmax_u16x2(diag, sc[r], E[r]);
+                    uint32_t H = __vmaxu2(t, F);
+                    uint32_t u = H - g.ngoe;
+                    uint32_t e1 = E[r] - (g.ngoe >> 2);
+                    E[r] = __vimax3_u16x2(e1, u, g.B);
+                    F = __viaddmax_u16x2(F, g.nge, u);
+                    diag = Hl[r];
+                    Hl[r] = H;
+                    if (r & 1) best = __vimax3_u16x2(best, Hprev, H); else Hprev = H;
+                }
+                continue;
+            }
             if (MODE == 6 || MODE == 7) {
                 // signed variants: relu folded into the add-max, H by a 2-input max, packed 16-bit add
 #pragma unroll
@@ -153,6 +169,7 @@ extern "C" int osw_calibrate(int device, double out[12]) {
     rc |= run_mode<6>(n_sms, g, &cyc); out[7] = warp_instr * 16 * 2 * 32 / cyc;       // signed relu variant
     rc |= run_mode<7>(n_sms, g, &cyc); out[8] = warp_instr * 16 * 2 * 32 / cyc;       // ... without max tracking
     rc |= run_mode<8>(n_sms, g, &cyc); out[9] = warp_instr * 16 * 2 * 32 / cyc;       // unsigned without max tracking
+    rc |= run_mode<9>(n_sms, g, &cyc); out[10] = warp_instr * 16 * 2 * 32 / cyc;      // clamped E, 2-input max for H
     clock_probe<<<1, 1>>>(g.cycles);
     unsigned long long cp[2] = {0, 1};
     if (cudaMemcpy(cp, g.cycles, sizeof cp, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -1;

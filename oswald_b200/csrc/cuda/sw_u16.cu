@@ -66,6 +66,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
 // profile reads: the profile is constant once built, so the compiler may schedule these freely
 __device__ __forceinline__ uint4 add4(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ uint4 lds128_const(uint32_t addr) {
@@ -100,12 +108,13 @@ sw_u16_kernel(const KArgs a) {
     constexpr int NC = NUM_CHAINS;              // independent row segments per lane
 
     extern __shared__ __align__(128) unsigned char smem[];
-    // layout: [profile copies][mailbox: WARPS*32 uint4][rings: WARPS*GROUPS*RING uint4]
+    // layout: [profile copies][mailbox: WARPS*32 uint4][rings: WARPS*GROUPS*RING uint4][out rings: WARPS*32 uint2]
     unsigned char *s_prof = smem;
     constexpr int TABLE_B = COPY_B * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0);
     constexpr int PROF_B = TABLE_B * (PD ? 2 : 1);           // PD: low-half table, then high-half table
     uint4 *s_mail = reinterpret_cast<uint4 *>(smem + PROF_B);
     uint4 *s_ring = s_mail + WARPS * 32;
+    uint2 *s_oring = reinterpret_cast<uint2 *>(s_ring + WARPS * GROUPS * RING);     // [WARPS][32] bottom rows of the last 32 steps
     __shared__ int s_mat[24 * 32];
     __shared__ uint32_t s_chunk[WARPS];
 
@@ -151,6 +160,7 @@ sw_u16_kernel(const KArgs a) {
     const uint32_t mail_self = (uint32_t)__cvta_generic_to_shared(s_mail + wib * 32 + lane);
     const uint32_t mail_up = mail_self - 16;     // lane-1's mailbox (unused when t == 0)
     const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(s_ring + (wib * GROUPS + grp) * RING);
+    const uint32_t oring_base = (uint32_t)__cvta_generic_to_shared(s_oring + wib * 32);      // (G == 32 when used)
     const uint32_t B2 = a.bias2, NGE = a.nge2, GOE2 = 0u - a.ngoe_word;
     constexpr uint32_t PAD_MSG = OSW_COL_PADBYTE | (OSW_COL_PADBYTE << 8);    // "no column": padding residue(s), no flags
     const bool multi_in = a.has_in != 0, has_out = a.has_out != 0;
@@ -223,7 +233,6 @@ sw_u16_kernel(const KArgs a) {
         for (int c = 0; c < NC; ++c) { diag[c] = B2; mid[c] = make_uint4(B2, B2, B2, PAD_MSG); }
         uint32_t seq = ck.seq0;
         uint2 *out_base = has_out ? p.bound + col0 : nullptr;
-        const uint32_t out_limit = t == G - 1 ? cols_padded : 0u;      // only the group's last lane stores
         sts128(mail_self, make_uint4(B2, B2, B2, PAD_MSG));
         __syncwarp();
 
@@ -306,10 +315,8 @@ sw_u16_kernel(const KArgs a) {
                 const uint32_t lf = msg[NC - 1].w;
                 const uint32_t Hbot = Hl[R - 1], Fbot = F[NC - 1], cmbot = cm[NC - 1];
                 run = __vmaxu2(run, cmbot);
-                if (has_out) {                       // (uniform) several passes: park this pass's bottom row
-                    const uint32_t col = step - (NC * G - 1);        // column the last segment just finished
-                    if (col < out_limit) __stcg(out_base + col, make_uint2(Hbot, Fbot));
-                }
+                if (has_out && t == G - 1)           // several passes: the group's last lane stages this pass's bottom row
+                    sts64(oring_base + i * 8, make_uint2(Hbot, Fbot));
                 if (lf & last_mask) {                // last lane of the group, last column of a sequence
                     const uint32_t lo = run & 0xffffu, hi = run >> 16;
                     const int sa = lo >= FLAG_THRESHOLD ? OSW_SCORE_FLAGGED : (int)(lo - a.bias);
@@ -330,6 +337,11 @@ sw_u16_kernel(const KArgs a) {
                 sts128(mail_self, make_uint4(Hbot, Fbot, cmbot, lf));
                 __syncwarp();
             }
+            if (has_out) {
+                // flush the 32 bottom-row entries of this block: step s finished column s - (NC*G - 1)
+                const uint32_t col = blk * 32 + lane - (NC * G - 1);
+                if (col < cols_padded) __stcg(out_base + col, lds64(oring_base + lane * 8));
+            }
             commit(blk + 1);
             __syncwarp();
         }
@@ -340,7 +352,7 @@ sw_u16_kernel(const KArgs a) {
 template <int G, int R, int THREADS, bool PD>
 int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
     const size_t prof = (prof_copy_bytes(G, R) * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0)) * (PD ? 2 : 1);
-    const size_t smem = prof + (size_t)(THREADS / 32) * 32 * 16 + (size_t)(THREADS / 32) * (32 / G) * RING * 16;
+    const size_t smem = prof + (size_t)(THREADS / 32) * 32 * 16 + (size_t)(THREADS / 32) * (32 / G) * RING * 16 + (size_t)(THREADS / 32) * 32 * 8;
     static bool configured[64] = {};          // the attribute is per device
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return OSW_E_CUDA;

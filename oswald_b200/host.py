@@ -226,7 +226,7 @@ def calibrate(device=0):
             "cells_per_sm_clk_step_imad": out[2], "imad_per_sm_clk": out[3], "sm_mhz": out[4],
             "cells_per_sm_clk_step_plain_sub": out[5], "cells_per_sm_clk_step_with_lds": out[6],
             "cells_per_sm_clk_step_signed_relu": out[7], "cells_per_sm_clk_step_signed_relu_nomax": out[8],
-            "cells_per_sm_clk_step_nomax": out[9]}
+            "cells_per_sm_clk_step_nomax": out[9], "cells_per_sm_clk_step_clamped_e": out[10]}
 
 
 MIX_CLASSES = ["VIADDMNMX.U16x2", "VIMNMX3.U16x2", "VIADD", "IMAD", "HMNMX2", "VIMNMX.U16x2", "VIMNMX.U32", "LOP3",
