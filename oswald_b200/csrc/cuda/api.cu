@@ -27,8 +27,11 @@ namespace {
 constexpr uint32_t MAX_LAUNCH_SLOTS = 4096;
 constexpr uint32_t FLAG_CAPACITY_MIN = 1u << 16;
 
+struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; };
+
 struct DevState {
     int dev = -1, n_sms = 0;
+    std::vector<LaunchRecord> trace;           // first-stage launches of the last search
     cudaStream_t st = nullptr, st2 = nullptr;      // st2: second lane for first-stage launches (tail overlap)
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -339,8 +342,8 @@ constexpr int MAX_PASSES = 2048;
 
 int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32_t *q_off, int nq,
                    const int8_t *matrix, int go, int ge, uint32_t top_r, bool want_all,
-                   const std::vector<OswPass> &passes, uint32_t *n_launch_slots, uint64_t *launches,
-                   uint64_t *padded_cells) {
+                   const std::vector<OswPass> &passes, const std::vector<OswPass> &wide,
+                   uint32_t *n_launch_slots, uint64_t *launches, uint64_t *padded_cells) {
     const osw_shard &s = d.shard;
     const uint64_t N = s.n_seqs;
     const size_t q_bytes = q_off[nq];
@@ -397,25 +400,54 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
     CK(cudaMemsetAsync(d.d_cycles, 0, MAX_LAUNCH_SLOTS * sizeof(unsigned long long), d.st));
 
     uint32_t slot = 0;
+    d.trace.clear();
     if (use_u16 && N) {
-        // One launch per pass, in order: a pass reads the bottom row the previous one parked (in
-        // place: a warp writes a chunk's columns behind the ones it still has to read).
-        for (const OswPass &ps : passes) {
+        auto launch = [&](const OswPass &ps, uint32_t first, uint32_t end, cudaStream_t st) -> int {
             if (slot >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
             U16Params up;
-            up.stream = d.d_stream; up.pair_stream = d.d_pair; up.chunks = d.d_chunks; up.n_chunks = s.n_chunks;
+            up.stream = d.d_stream; up.pair_stream = d.d_pair; up.chunks = d.d_chunks;
+            up.chunk_first = first; up.chunk_end = end;
             up.queries = d.d_queries; up.q_off = d.d_qoff; up.matrix = d.d_matrix;
             up.scores = d.d_scores; up.n_seqs = N;
             up.bound = d.d_bound[0];
             up.gap_open_extend = go + ge; up.gap_extend = ge;
             up.chunk_counter = d.d_counters + 1 + slot;
             up.cycle_acc = d.d_cycles + slot;
-            if ((rc = osw_launch_u16(up, ps, d.n_sms, d.st)) != OSW_OK) {
-                cuda_fail(cudaGetLastError(), "sw_u16 launch", __LINE__);
-                return rc;
-            }
+            int rc2 = osw_launch_u16(up, ps, d.n_sms, st);
+            if (rc2 != OSW_OK) { cuda_fail(cudaGetLastError(), "sw_u16 launch", __LINE__); return rc2; }
+            uint64_t cols = 0;
+            if (first == 0 && end == s.n_chunks) cols = ps.pair_db ? s.pair_cols : s.n_residues;
+            else for (uint32_t k = first; k < end; ++k) cols += ps.pair_db ? s.chunks[k].n_pair_cols : s.chunks[k].n_cols;
+            d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols});
             ++slot; ++*launches;
-            *padded_cells += (uint64_t)ps.G * ps.R * 2 * (ps.pair_db ? s.pair_cols : s.n_residues);
+            *padded_cells += (uint64_t)ps.G * ps.R * 2 * cols;
+            return OSW_OK;
+        };
+        // A narrow plan (G < 32: several sequences per warp) leaves a very long sequence to a few
+        // lanes, and that chunk's latency would outlast the rest of the launch.  Such chunks (they
+        // lead the descending list) go to a second, concurrent launch with one sequence per warp:
+        // 32 lanes sweep the sequence's anti-diagonals (the intra-task path).
+        uint32_t n_long = 0;
+        if (passes.size() == 1 && passes[0].G < 32 && wide.size() == 1) {
+            const OswPass &ps = passes[0];
+            const double cols_total = (double)(ps.pair_db ? s.pair_cols : s.n_residues);
+            const double ideal_cycles = 2.0 * ps.G * ps.R * cols_total / (23.0 * d.n_sms);
+            const double step_latency = ps.R / 2.0 * 14.0 + 60.0;
+            const double limit = std::max(512.0, 0.5 * ideal_cycles / step_latency);
+            while (n_long < s.n_chunks && (double)(ps.pair_db ? s.chunks[n_long].n_pair_cols : s.chunks[n_long].n_cols) > limit) ++n_long;
+        }
+        if (n_long) {
+            CK(cudaEventRecord(d.ev_fork, d.st));
+            CK(cudaStreamWaitEvent(d.st2, d.ev_fork, 0));
+            if ((rc = launch(wide[0], 0, n_long, d.st2)) != OSW_OK) return rc;
+            if (n_long < s.n_chunks && (rc = launch(passes[0], n_long, s.n_chunks, d.st)) != OSW_OK) return rc;
+            CK(cudaEventRecord(d.ev_join, d.st2));
+            CK(cudaStreamWaitEvent(d.st, d.ev_join, 0));
+        } else {
+            // One launch per pass, in order: a pass reads the bottom row the previous one parked (in
+            // place: a warp writes a chunk's columns behind the ones it still has to read).
+            for (const OswPass &ps : passes)
+                if ((rc = launch(ps, 0, s.n_chunks, d.st)) != OSW_OK) return rc;
         }
         CK(cudaEventRecord(d.ev[1], d.st));
         *launches += osw_collect_flagged(d.d_scores, N, nq, d.d_pairs, d.d_counters, flag_cap, d.st);
@@ -439,15 +471,20 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
     for (int q = 0; q < nq; ++q)
         if (q_off[q + 1] < q_off[q] || q_off[q + 1] - q_off[q] > OSW_MAX_QUERY_LEN) return OSW_E_ARG;
     const double t_wall0 = now_ms();
-    std::vector<OswPass> passes;
+    std::vector<OswPass> passes, wide;
     if (c->kernel_mask & OSW_K_U16) {
         std::vector<uint32_t> q_len((size_t)nq);
         for (int q = 0; q < nq; ++q) q_len[q] = q_off[q + 1] - q_off[q];
         passes.resize(MAX_PASSES);
         const int mode = (c->kernel_mask & OSW_K_PAIR_DB) ? OSW_PLAN_PAIR_DB : (c->kernel_mask & OSW_K_TWO_TRACK) ? OSW_PLAN_TWO_TRACK : OSW_PLAN_AUTO;
-        const int n_pass = osw_plan_passes(q_len.data(), nq, passes.data(), MAX_PASSES, mode);
+        const int n_pass = osw_plan_passes(q_len.data(), nq, passes.data(), MAX_PASSES, mode, 4);
         if (n_pass < 0) { snprintf(g_err, sizeof g_err, "the queries need more than %d passes", MAX_PASSES); return OSW_E_ARG; }
         passes.resize((size_t)n_pass);
+        if (n_pass == 1 && passes[0].G < 32) {        // one-sequence-per-warp variant of the same plan, for very long sequences
+            wide.resize(4);
+            const int n_wide = osw_plan_passes(q_len.data(), nq, wide.data(), 4, passes[0].pair_db ? OSW_PLAN_PAIR_DB : OSW_PLAN_TWO_TRACK, 32);
+            wide.resize(n_wide == 1 ? 1 : 0);
+        }
     }
     const bool use_u16 = (c->kernel_mask & OSW_K_U16) != 0;
     uint64_t launches = 0, padded = 0, rescored = 0;
@@ -456,7 +493,7 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
     // ---- phase 1: first stage on every GPU ------------------------------------------------
     for (int i = 0; i < c->n_dev; ++i) {
         int rc = enqueue_search(c, c->devs[i], queries, q_off, nq, matrix, go, ge, (uint32_t)top_r,
-                                all_scores != nullptr, passes, &slots[i], &launches, &padded);
+                                all_scores != nullptr, passes, wide, &slots[i], &launches, &padded);
         if (rc != OSW_OK) return rc;
     }
     const double t_h2d = now_ms();
@@ -523,11 +560,11 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
         if (i == 0) for (uint32_t k = 0; k < slots[i]; ++k) tm.sm_cycles += d.h_cycles[k];
         if (i == 0 && getenv("OSW_TRACE")) {
             // per-launch report: geometry, elapsed SM cycles, padded cell updates per SM-cycle
-            for (uint32_t k = 0; k < slots[i] && k < passes.size(); ++k) {
-                const OswPass &ps = passes[k];
-                const double cells = 2.0 * ps.G * ps.R * (double)(ps.pair_db ? d.shard.pair_cols : d.shard.n_residues);
-                fprintf(stderr, "osw trace: pass %u/%zu G=%d R=%d in=%d out=%d pairdb=%d  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
-                        k + 1, passes.size(), ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db,
+            for (uint32_t k = 0; k < slots[i] && k < d.trace.size(); ++k) {
+                const LaunchRecord &lr = d.trace[k];
+                const double cells = 2.0 * lr.G * lr.R * (double)lr.cols;
+                fprintf(stderr, "osw trace: launch %u/%zu G=%d R=%d in=%d out=%d pairdb=%d chunks [%u,%u)  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
+                        k + 1, d.trace.size(), lr.G, lr.R, lr.has_in, lr.has_out, lr.pair_db, lr.first, lr.end,
                         (unsigned long long)(d.h_cycles[k] / d.n_sms), cells / (double)d.h_cycles[k]);
             }
         }
@@ -566,7 +603,7 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
     tm.launches = launches;
     tm.db_stream_bytes = 0;
     for (int i = 0; i < c->n_dev; ++i)
-        for (const OswPass &ps : passes) tm.db_stream_bytes += ps.pair_db ? 2 * c->devs[i].shard.pair_cols : c->devs[i].shard.stream_bytes;
+        for (const LaunchRecord &lr : c->devs[i].trace) tm.db_stream_bytes += (lr.pair_db ? 2 : 1) * lr.cols;
     if (timing) *timing = tm;
     return OSW_OK;
 }

@@ -54,13 +54,14 @@ struct OswPass {
 #define OSW_PLAN_AUTO 0
 #define OSW_PLAN_TWO_TRACK 1
 #define OSW_PLAN_PAIR_DB 2
-extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes, int mode);
+// min_g: smallest group width allowed (4 = no restriction; 32 = one sequence per warp).
+extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes, int mode, int min_g);
 
 struct U16Params {
     const uint8_t   *stream;
     const uint8_t   *pair_stream; // two bytes per column (pair-database mode)
     const osw_chunk *chunks;     // descending-length order
-    uint32_t         n_chunks;
+    uint32_t         chunk_first, chunk_end;   // the launch works on chunks [chunk_first, chunk_end)
     const uint8_t   *queries;    // all queries back to back (codes)
     const uint32_t  *q_off;      // [nq+1]
     const int8_t    *matrix;

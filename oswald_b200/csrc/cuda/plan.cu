@@ -58,7 +58,7 @@ int lanes_needed(const Track &tr, const uint32_t *q_len, size_t cur, uint32_t do
 // Pair-database mode keeps two score tables in shared memory: with 32 lanes at most 28 rows each.
 static int pd_rmax(int G) { return G == 32 ? 28 : 40; }
 
-extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes, int mode) {
+extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes, int mode, int min_g) {
     if (!q_len || nq < 1 || !out || max_passes < 1) return -1;
     if (const char *e = getenv("OSW_RMAX")) {
         const int v = atoi(e);
@@ -112,7 +112,7 @@ extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int 
                 if (kR[ri] > kRmax || (pair_db && kR[ri] > pd_rmax(kG[gi]))) continue;
                 const int need = std::max(lanes_needed(tr[0], q_len, cur[0], done[0], kR[ri]),
                                           lanes_needed(tr[1], q_len, cur[1], done[1], kR[ri]));
-                if (need > kG[gi]) continue;
+                if (need > kG[gi] || kG[gi] < min_g) continue;
                 if (n > 0 && kG[gi] != 32) continue;            // a continued query keeps the 32-lane array
                 const uint64_t cost = (uint64_t)kG[gi] * (kR[ri] + 3);
                 if (cost < best) { best = cost; G = kG[gi]; R = kR[ri]; }

@@ -175,11 +175,11 @@ sw_u16_kernel(const KArgs a) {
         // ---- fetch one chunk per group ---------------------------------------------------
         if (lane == 0) s_chunk[wib] = atomicAdd(p.chunk_counter, (uint32_t)GROUPS);
         __syncwarp();
-        const uint32_t cbase = s_chunk[wib];
+        const uint32_t cbase = p.chunk_first + s_chunk[wib];
         __syncwarp();
-        if (cbase >= p.n_chunks) break;
+        if (cbase >= p.chunk_end) break;
         const uint32_t ci = cbase + grp;
-        const bool have = ci < p.n_chunks;
+        const bool have = ci < p.chunk_end;
         osw_chunk ck;
         if (have) ck = p.chunks[ci];
         else { ck.stream_off = 0; ck.n_cols = 0; ck.n_seqs = 0; ck.seq0 = 0; ck.canon0 = 0; ck.pair_off = 0; ck.n_pair_cols = 0; }

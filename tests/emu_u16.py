@@ -135,12 +135,12 @@ class Pass(C.Structure):
 PLAN_AUTO, PLAN_TWO_TRACK, PLAN_PAIR_DB = 0, 1, 2
 
 
-def plan_passes(lib, q_lens, max_passes=256, mode=PLAN_TWO_TRACK):
-    lib.osw_plan_passes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+def plan_passes(lib, q_lens, max_passes=256, mode=PLAN_TWO_TRACK, min_g=4):
+    lib.osw_plan_passes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.osw_plan_passes.restype = C.c_int
     arr = (C.c_uint32 * len(q_lens))(*q_lens)
     out = (Pass * max_passes)()
-    n = lib.osw_plan_passes(arr, len(q_lens), out, max_passes, mode)
+    n = lib.osw_plan_passes(arr, len(q_lens), out, max_passes, mode, min_g)
     assert n >= 0
     return [out[i] for i in range(n)]
 
