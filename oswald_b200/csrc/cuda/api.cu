@@ -1,8 +1,8 @@
 // api.cu - the C ABI (include/oswald_cuda.h): context, database upload, search orchestration.
 //
-// One DevState per GPU: its shard of the chunk streams resident in HBM, one stream, events.
+// One DevState per GPU: its shard of the chunk streams resident in HBM, streams, events.
 // osw_search enqueues, per GPU and without host synchronisation in between:
-//   score clear -> first-stage launches (one per query pair and pass) -> flagged-pair scan,
+//   score clear -> first-stage launches (one per pass of the plan, plan.cu) -> flagged-pair scan,
 // then (after reading each GPU's flagged count) 32-bit re-score -> top-r radix select,
 // and only then waits for all GPUs, orders the r keys per query on the host and merges the
 // GPUs' lists (the reference's sort_scores order, utils.c:3-86).
@@ -32,7 +32,7 @@ struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; u
 struct DevState {
     int dev = -1, n_sms = 0;
     std::vector<LaunchRecord> trace;           // first-stage launches of the last search
-    cudaStream_t st = nullptr, st2 = nullptr;      // st2: second lane for first-stage launches (tail overlap)
+    cudaStream_t st = nullptr, st2 = nullptr;      // st2: concurrent launch for very long chunks
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // database shard
@@ -47,7 +47,7 @@ struct DevState {
     uint32_t *d_qoff = nullptr; size_t qoff_cap = 0;
     int8_t *d_matrix = nullptr;
     int2 *d_scratch = nullptr; size_t scratch_cap = 0;
-    uint2 *d_bound[2] = {nullptr, nullptr};
+    uint2 *d_bound = nullptr;                  // bottom rows handed from pass to pass (in place)
     uint2 *d_pairs = nullptr; uint32_t pairs_cap = 0;
     uint32_t *d_counters = nullptr;            // [0] flagged count, [1..] chunk counters per launch
     unsigned long long *d_task_counter = nullptr;   // [0] i32 queue, [1] n_tasks mirror
@@ -86,9 +86,9 @@ void free_db(DevState &d) {
     if (d.h_pair) cudaFreeHost(d.h_pair);
     d.h_pair = nullptr;
     cudaFree(d.d_stream); cudaFree(d.d_chunks); cudaFree(d.d_canon); cudaFree(d.d_seq_off); cudaFree(d.d_seq_len);
-    cudaFree(d.d_bound[0]); cudaFree(d.d_bound[1]);
+    cudaFree(d.d_bound);
     d.d_stream = nullptr; d.d_chunks = nullptr; d.d_canon = nullptr; d.d_seq_off = nullptr; d.d_seq_len = nullptr;
-    d.d_bound[0] = d.d_bound[1] = nullptr;
+    d.d_bound = nullptr;
     if (d.h_stream) cudaFreeHost(d.h_stream);
     d.h_stream = nullptr;
     osw_shard_free(&d.shard);
@@ -382,10 +382,10 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
         flag_cap = d.pairs_cap;
         bool need_bound = false;
         for (const OswPass &p : passes) need_bound |= p.has_in || p.has_out;
-        if (need_bound && !d.d_bound[0]) {
+        if (need_bound && !d.d_bound) {
             const size_t cols = std::max<uint64_t>(std::max<uint64_t>(s.stream_bytes, s.pair_cols), 1);
-            CK(cudaMalloc(&d.d_bound[0], cols * sizeof(uint2)));
-            CK(cudaMemsetAsync(d.d_bound[0], 0, cols * sizeof(uint2), d.st));
+            CK(cudaMalloc(&d.d_bound, cols * sizeof(uint2)));
+            CK(cudaMemsetAsync(d.d_bound, 0, cols * sizeof(uint2), d.st));
         }
     }
 
@@ -409,7 +409,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             up.chunk_first = first; up.chunk_end = end;
             up.queries = d.d_queries; up.q_off = d.d_qoff; up.matrix = d.d_matrix;
             up.scores = d.d_scores; up.n_seqs = N;
-            up.bound = d.d_bound[0];
+            up.bound = d.d_bound;
             up.gap_open_extend = go + ge; up.gap_extend = ge;
             up.chunk_counter = d.d_counters + 1 + slot;
             up.cycle_acc = d.d_cycles + slot;

@@ -4,37 +4,48 @@
 // :937-1030, and the FPGA kernel device/sw.cl) - not their structure.
 //
 // Work decomposition
-//   * Every 32-bit word carries two independent DP problems against the SAME database residue:
-//     the low half works on rows of track 0, the high half on rows of track 1 (plan.cu lays the
-//     queries end to end on the two tracks, each query starting on a lane boundary).  A launch
-//     ("pass") covers the next `G*R` rows of both tracks against every database chunk.  One
-//     shared-memory read of the pair profile
+//   * Every 32-bit word carries two independent DP problems.  Normally both are against the SAME
+//     database residue: the low half works on rows of query track 0, the high half on rows of
+//     track 1 (plan.cu lays the queries end to end on the two tracks, each query starting on a
+//     lane boundary).  A launch ("pass") covers the next `G*R` rows of both tracks against every
+//     database chunk, and one shared-memory read of the pair profile
 //         prof[residue][row] = (M[track0[row]][residue], M[track1[row]][residue])
-//     serves two cell updates and is bank-conflict free by construction (see below).
+//     serves two cell updates, bank-conflict free by construction: the table is laid out
+//     [residue][quad of rows] with a 128-byte multiple as row pitch and an odd number of quads per
+//     lane, so the 8 lanes of a quarter warp hit 8 different 16-byte bank groups whatever their
+//     residues are.  In pair-database mode (template flag PD; single or lopsided query sets) both
+//     halves work on the same query rows against two database sequences zipped in the pair
+//     stream, and a row's score word is the sum of a low-half and a high-half table entry.
 //   * G lanes (4, 8, 16 or 32) form a systolic array over the query rows: lane t owns rows
-//     t*R .. t*R+R-1, with H(left), E of its rows in registers.  A chunk's column stream flows
-//     through the array, lane t working on column (step - t); sequences follow one another
-//     without draining the array (flags in the stream byte restart the state).
+//     t*R .. t*R+R-1 (H of the previous column and E in registers), swept as two independent
+//     segments one column apart (two dependency chains per thread keep the DPX pipe fed).  A
+//     chunk's column stream flows through the array; sequences follow one another without
+//     draining it (the FIRST flag of a column restarts a lane's state).  With G = 32 one warp
+//     sweeps the anti-diagonals of one sequence at a time - the intra-task path for very long
+//     sequences; with G < 32 several sequences share a warp (inter-task).
 //   * Per step a lane reads a 16-byte message {H, F of the row above, running column maximum,
-//     residue+flags}, sweeps its R rows, and writes the same message for the lane below
-//     through a per-warp shared-memory mailbox.  Lane 0 of a group reads its messages from a
-//     ring the group fills 32 columns ahead from the chunk stream (128-bit coalesced loads);
-//     when the query needs several passes (more than 32*R rows) the ring also carries the
-//     previous pass's bottom row, and the last lane stores this pass's bottom row.
-//   * The last lane of a group sees, per column, the maximum over all rows; it keeps the
-//     running maximum of the sequence and publishes it at the column flagged LAST.
+//     residue(s)+flags}, sweeps its R rows, and writes the same message for the lane below through
+//     a per-warp shared-memory mailbox.  Lane 0 of a group reads its messages from a ring the
+//     group fills 32 columns ahead from the chunk stream (coalesced loads); when the plan has
+//     several passes the ring also carries the previous pass's bottom row (H, F) and the last
+//     lane stages this pass's bottom row in shared memory, flushed every 32 steps (in place: a
+//     warp writes a chunk's columns behind the ones it still has to read).
+//   * A lane that holds a query's first row replaces the message from above by "no row"; the
+//     last lane of a query in the pass sees, per column, the maximum over the query's rows, keeps
+//     the running maximum of the sequence and publishes it (atomicMax into the score matrix) at
+//     the column flagged LAST.
 //
-// Arithmetic: unsigned 16-bit lanes with a bias B (value v is stored as v+B), so that
-//   t  = VIADDMNMX.U16x2(Hdiag, score, E)      max(Hdiag + s, E)
+// Arithmetic: unsigned 16-bit halves with a bias B = go + 2*ge + 32 (value v is stored as v+B):
+//   t  = VIADDMNMX.U16x2(Hdiag, score, E)      max(Hdiag + s, E)   (the add wraps: s is two's complement)
 //   H  = VIMNMX3.U16x2(t, F, B)                max(t, F, 0)
-//   u  = IMAD(H, 1, -(go+ge) packed)           H - (go+ge): no borrow between halves since
-//                                              H >= B >= go+ge; runs on the FMA pipe
+//   u  = H - (go+ge | go+ge << 16)             one 32-bit subtract (VIADD, co-issues with the DPX
+//                                              pipe): no borrow between halves since H >= B >= go+ge
 //   E  = VIADDMNMX.U16x2(E, -ge, u)            max(E - ge, u)
 //   F  = VIADDMNMX.U16x2(F, -ge, u)
 //   cm = VIMNMX3.U16x2(cm, H_even, H_odd)      every second row
-// i.e. 4.5 ALU-pipe + 1 FMA-pipe instructions per word = per two cell updates.  A sequence
-// whose biased maximum reaches 65504 may have wrapped and is flagged for the 32-bit kernel
-// (scores grow by at most 17 per cell, so a wrap cannot be missed).
+// i.e. 4.5 DPX-pipe instructions per word = per two cell updates.  A sequence whose biased
+// maximum reaches 65504 may have wrapped and is flagged for the 32-bit kernel (scores grow by at
+// most 17 per cell, so a wrap cannot be missed).
 #include "osw_internal.h"
 #include <stdlib.h>
 #include <string.h>
