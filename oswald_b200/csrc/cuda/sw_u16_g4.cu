@@ -1,0 +1,5 @@
+// sw_u16_g4.cu - instances of the first-stage kernel with G = 4 lanes per database sequence.
+#include "sw_u16_kernel.cuh"
+namespace osw_u16 {
+int launch_g4(int R, const KArgs &a, int n_sms, cudaStream_t st) { return launch_g<4>(R, a, n_sms, st); }
+}

@@ -1,0 +1,5 @@
+// sw_u16_g8.cu - instances of the first-stage kernel with G = 8 lanes per database sequence.
+#include "sw_u16_kernel.cuh"
+namespace osw_u16 {
+int launch_g8(int R, const KArgs &a, int n_sms, cudaStream_t st) { return launch_g<8>(R, a, n_sms, st); }
+}
