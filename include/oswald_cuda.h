@@ -109,7 +109,8 @@ int osw_db_stats(const osw_ctx *ctx, uint64_t *n_seqs_local, uint64_t *residues_
  * all_scores: nullable; caller-owned nq*n_seqs int32 (n_seqs = the canonical database size);
  *          entries of sequences held by this context are written at [q*n_seqs + index],
  *          others are left untouched.
- * Blocking; not re-entrant per context. */
+ * Residue codes must be 0..23 and matrix entries within -32..31 (the reference's tables span
+ * -17..17), otherwise OSW_E_ARG.  Blocking; not re-entrant per context. */
 int osw_search(osw_ctx *ctx, const uint8_t *queries, const uint32_t *q_off, int nq,
                const int8_t *matrix, int gap_open, int gap_extend, int top_r,
                osw_hit *hits, uint32_t *n_hits, int32_t *all_scores, osw_timing *timing);

@@ -260,8 +260,9 @@ extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *
     for (int i = 0; i < c->n_dev; ++i) {
         DevState &d = c->devs[i];
         free_db(d);
-        if (osw_shard_build(residues, offsets, n_seqs, (uint32_t)shard_rank * c->n_dev + i, n_shards, chunk_cols, &d.shard) != 0)
-            return OSW_E_NOMEM;
+        const int brc = osw_shard_build(residues, offsets, n_seqs, (uint32_t)shard_rank * c->n_dev + i, n_shards, chunk_cols, &d.shard);
+        if (brc == -2) { snprintf(g_err, sizeof g_err, "the database holds a residue code outside 0..23"); return OSW_E_ARG; }
+        if (brc != 0) return OSW_E_NOMEM;
         const osw_shard &s = d.shard;
         CK(cudaSetDevice(d.dev));
         CK(cudaMalloc(&d.d_stream, s.stream_bytes ? s.stream_bytes : 1));
@@ -470,6 +471,11 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
     if (!c->db_loaded) return OSW_E_STATE;
     for (int q = 0; q < nq; ++q)
         if (q_off[q + 1] < q_off[q] || q_off[q + 1] - q_off[q] > OSW_MAX_QUERY_LEN) return OSW_E_ARG;
+    for (uint32_t k = q_off[0]; k < q_off[nq]; ++k)
+        if (queries[k] > 23) { snprintf(g_err, sizeof g_err, "query residue code %u is outside 0..23", queries[k]); return OSW_E_ARG; }
+    // the 16-bit kernel's bias and wrap detection assume |score| <= 31 (the reference's tables span -17..17)
+    for (int k = 0; k < 24 * 32; ++k)
+        if (matrix[k] < -32 || matrix[k] > 31) { snprintf(g_err, sizeof g_err, "substitution score %d is outside -32..31", matrix[k]); return OSW_E_ARG; }
     const double t_wall0 = now_ms();
     std::vector<OswPass> passes, wide;
     if (c->kernel_mask & OSW_K_U16) {

@@ -49,7 +49,7 @@ static void tally_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t 
 }
 
 typedef struct { uint32_t shard, n_shards; const uint8_t *res; const uint64_t *off; osw_shard *s;
-                 uint64_t seq_cursor, byte_cursor, pair_cursor; uint32_t chunk_cursor; } fill_t;
+                 uint64_t seq_cursor, byte_cursor, pair_cursor; uint32_t chunk_cursor; int bad_residue; } fill_t;
 static void fill_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t cols) {
     fill_t *f = (fill_t *)u;
     if (c % f->n_shards != f->shard) return;
@@ -64,7 +64,10 @@ static void fill_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t c
         const uint8_t *src = f->res + f->off[i];
         uint64_t l = f->seq_cursor++;
         s->canon[l] = (uint32_t)i; s->seq_off[l] = (uint64_t)(p - s->stream); s->seq_len[l] = (uint32_t)len;
-        for (uint64_t k = 0; k < len; ++k) p[k] = (uint8_t)(src[k] & OSW_COL_CODE);
+        for (uint64_t k = 0; k < len; ++k) {
+            if (src[k] > 23) f->bad_residue = 1;               /* codes are 0..23 (sequences.c:163-175) */
+            p[k] = (uint8_t)(src[k] & OSW_COL_CODE);
+        }
         if (len) { p[0] |= OSW_COL_FIRST; p[len - 1] |= OSW_COL_LAST; }
         p += len;
     }
@@ -117,6 +120,7 @@ int osw_shard_build(const uint8_t *residues, const uint64_t *offsets, uint64_t n
     fill_t f; memset(&f, 0, sizeof f);
     f.shard = shard; f.n_shards = n_shards; f.res = residues; f.off = offsets; f.s = out;
     walk_chunks(offsets, n_seqs, chunk_cols, fill_cb, &f);
+    if (f.bad_residue) { osw_shard_free(out); return -2; }
     return 0;
 }
 

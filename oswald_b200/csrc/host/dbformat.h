@@ -70,7 +70,7 @@ typedef struct osw_shard {
 uint64_t osw_count_chunks(const uint64_t *offsets, uint64_t n_seqs, uint32_t chunk_cols);
 
 /* Build shard `shard` of `n_shards` (chunk c belongs to shard c mod n_shards).
- * Returns 0, or -1 on allocation failure / bad arguments. */
+ * Returns 0, -1 on allocation failure / bad arguments, -2 if a residue code is not in 0..23. */
 int osw_shard_build(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
                     uint32_t shard, uint32_t n_shards, uint32_t chunk_cols, osw_shard *out);
 void osw_shard_free(osw_shard *s);

@@ -44,8 +44,11 @@ typedef struct osw_options {
 
 void program_arguments_processing(int argc, char **argv, osw_options *opt);
 
-/* residue code of a FASTA letter, reference sequences.c:163-175 */
+/* residue code of a FASTA letter, reference sequences.c:163-175.  The reference does not
+ * validate its input (anything but A-Z is undefined behaviour there); here such bytes become the
+ * dummy residue 23, like J/O/U. */
 static inline uint8_t osw_encode_letter(unsigned char c) {
+    if (c < 'A' || c > 'Z') return 23;
     unsigned x = (c == 'J' || c == 'O' || c == 'U') ? 'Z' + 1 : c;
     return (uint8_t)(x - 'A' - (x > 'J') - (x > 'O') - (x > 'U'));
 }

@@ -251,3 +251,25 @@ def test_two_gpus_in_one_context(built):
         s.load_db(db, max_chunk_residues=1024)
         assert s.stats()["n_seqs"] == db.n_seqs
         check(s, db, q, "blosum62", 10, 2, 10)
+
+
+def test_invalid_inputs_are_rejected(searcher):
+    rng = np.random.default_rng(2)
+    db = make_db(rand_seqs(rng, 50, 5, 60))
+    searcher.load_db(db)
+    searcher.set_kernels(capi.OSW_K_DEFAULT)
+    q = ob.Queries.from_list([AA[rng.integers(0, 20, size=30)]])
+    bad_q = ob.Queries(np.full(30, 24, dtype=np.uint8), q.offsets)
+    with pytest.raises(capi.OswError):
+        searcher.search(bad_q, ob.matrix("blosum62"), 10, 2, top=5)
+    big = ob.matrix("blosum62").copy()
+    big[0] = 100
+    with pytest.raises(capi.OswError):
+        searcher.search(q, big, 10, 2, top=5)
+    with pytest.raises(capi.OswError):
+        searcher.search(q, ob.matrix("blosum62"), 256, 2, top=5)
+    bad_db = ob.Database(np.full(40, 30, dtype=np.uint8), np.array([0, 40], dtype=np.uint64))
+    with pytest.raises(capi.OswError):
+        searcher.load_db(bad_db)
+    searcher.load_db(db)                       # the context stays usable
+    check(searcher, db, q, "blosum62", 10, 2, 5)
