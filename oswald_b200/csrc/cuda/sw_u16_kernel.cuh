@@ -62,6 +62,7 @@ __host__ __device__ constexpr int prof_quads(int G, int R) { return (G * pitch_q
 __host__ __device__ constexpr int prof_copies(int G) { return G == 4 ? 2 : 1; }
 __host__ __device__ constexpr size_t prof_copy_bytes(int G, int R) { return (size_t)24 * prof_quads(G, R) * 16; }
 __host__ __device__ constexpr int block_threads(int R) { return R > 32 ? 384 : 512; }
+// (OSW_EXP_* macros: timing experiments only - each one breaks the results; never set in the product build.)
 // A lane's R rows are swept as NUM_CHAINS independent segments (segment c works one column
 // behind segment c-1): two dependency chains per thread keep the DPX pipe fed.
 #ifndef OSW_NUM_CHAINS
@@ -256,7 +257,11 @@ sw_u16_kernel(const KArgs a) {
                 const uint32_t step = blk * 32 + i;
                 const uint32_t in_addr = t == 0 ? ring_base + (step & (RING - 1)) * 16 : mail_up;
                 uint4 msg[NC];
+#ifdef OSW_EXP_NO_MAIL
+                msg[0] = make_uint4(B2 + step, B2, B2, (step * 7) % 20);
+#else
                 msg[0] = lds128(in_addr);
+#endif
 #ifndef OSW_EXPERIMENT_NO_KEEP
                 msg[0].x = (msg[0].x & keep) | (B2 & ~keep);      // a query's first lane has no row above it
                 msg[0].y = (msg[0].y & keep) | (B2 & ~keep);
@@ -265,13 +270,25 @@ sw_u16_kernel(const KArgs a) {
 #pragma unroll
                 for (int c = 1; c < NC; ++c) msg[c] = mid[c];
                 uint32_t paddr[NC], paddr_hi[NC];
+                // a column flagged FIRST restarts the DP state of the segment that works on it (one
+                // test for all segments: the restart is rare)
+                uint32_t any_first = 0;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) any_first |= msg[c].w;
+#ifndef OSW_EXP_NO_FIRST
+                if (any_first & OSW_COL_FIRST) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        if (msg[c].w & OSW_COL_FIRST) {
+#pragma unroll
+                            for (int r = 4 * seg_begin(R, NC, c); r < 4 * seg_begin(R, NC, c + 1); ++r) { Hl[r] = B2; E[r] = B2; }
+                            diag[c] = B2;
+                        }
+                    }
+                }
+#endif
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    if (msg[c].w & OSW_COL_FIRST) {
-#pragma unroll
-                        for (int r = 4 * seg_begin(R, NC, c); r < 4 * seg_begin(R, NC, c + 1); ++r) { Hl[r] = B2; E[r] = B2; }
-                        diag[c] = B2;
-                    }
                     paddr[c] = prof_lane + (msg[c].w & OSW_COL_CODE) * PITCH_B + seg_begin(R, NC, c) * 16;
                     paddr_hi[c] = PD ? prof_lane + TABLE_B + ((msg[c].w >> 8) & OSW_COL_CODE) * PITCH_B + seg_begin(R, NC, c) * 16 : 0u;
                 }
@@ -312,7 +329,11 @@ sw_u16_kernel(const KArgs a) {
                                 E[r] = __viaddmax_u16x2(E[r], NGE, u);
                                 F[c] = __viaddmax_u16x2(F[c], NGE, u);
                                 Hl[r] = H;
+#ifdef OSW_EXP_NO_CM
+                                if (r == 0) cm[c] = H;
+#else
                                 if (rr & 1) cm[c] = __vimax3_u16x2(cm[c], Heven[c], H); else Heven[c] = H;
+#endif
                             }
                         }
                     }
@@ -346,9 +367,13 @@ sw_u16_kernel(const KArgs a) {
                     ++seq;
                     run = B2;
                 }
+#ifndef OSW_EXP_NO_SYNC
                 __syncwarp();
+#endif
                 sts128(mail_self, make_uint4(Hbot, Fbot, cmbot, lf));
+#ifndef OSW_EXP_NO_SYNC
                 __syncwarp();
+#endif
             }
             if (has_out) {
                 // flush the 32 bottom-row entries of this block: step s finished column s - (NC*G - 1)
