@@ -369,10 +369,6 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
     if (want_all && (rc = grow_pinned(&d.h_scores, &d.h_scores_cap, (size_t)nq * (N ? N : 1))) != OSW_OK) return rc;
 
     const bool use_u16 = (c->kernel_mask & OSW_K_U16) != 0;
-    // 32-bit kernel geometry and scratch
-    const int i32_blocks = d.n_sms * 4;
-    const size_t warps = (size_t)i32_blocks * (osw_i32_block_threads() / 32);
-    if ((rc = grow(&d.d_scratch, &d.scratch_cap, warps * (s.max_len ? s.max_len : 1))) != OSW_OK) return rc;
     uint32_t flag_cap = 0;
     if (use_u16) {
         uint64_t want = std::max<uint64_t>(FLAG_CAPACITY_MIN, (uint64_t)nq * N / 64);
@@ -515,6 +511,13 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
         ip.n_seqs = N; ip.scores = d.d_scores; ip.scratch = d.d_scratch; ip.max_len = s.max_len ? s.max_len : 1;
         ip.gap_open_extend = go + ge; ip.gap_extend = ge; ip.task_counter = d.d_task_counter;
         const int i32_blocks = d.n_sms * 4;
+        // per-warp scratch of the 32-bit kernel (a pass's bottom row): allocated when first needed
+        auto need_scratch = [&]() -> int {
+            const size_t warps = (size_t)i32_blocks * (osw_i32_block_threads() / 32);
+            int rc2 = grow(&d.d_scratch, &d.scratch_cap, warps * (s.max_len ? s.max_len : 1));
+            ip.scratch = d.d_scratch;
+            return rc2;
+        };
         if (use_u16) {
             // the flagged count was copied to h_counts in phase 1; wait for it (tiny sync per GPU)
             CK(cudaStreamSynchronize(d.st));
@@ -525,11 +528,15 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
             }
             rescored += n_flag;
             if (n_flag) {
+                int rc2 = need_scratch();
+                if (rc2 != OSW_OK) return rc2;
                 ip.pairs = d.d_pairs; ip.n_tasks = n_flag;
                 osw_launch_i32(ip, (int)std::min<uint64_t>((uint64_t)i32_blocks, ((uint64_t)n_flag + 7) / 8), d.st);
                 ++launches;
             }
         } else if (N) {
+            int rc2 = need_scratch();
+            if (rc2 != OSW_OK) return rc2;
             ip.pairs = nullptr; ip.n_tasks = (uint64_t)nq * N;
             rescored += ip.n_tasks;
             osw_launch_i32(ip, i32_blocks, d.st);
