@@ -10,7 +10,9 @@ static uint64_t walk_chunks(const uint64_t *off, uint64_t n, uint32_t chunk_cols
     uint64_t c = 0, first = 0, cols = 0;
     for (uint64_t i = 0; i < n; ++i) {
         uint64_t len = off[i + 1] - off[i];
-        if (i > first && cols + len > chunk_cols) {
+        /* empty sequences (they lead the ascending order) have no column, so they cannot share a
+         * chunk with real ones: the kernel counts sequences by their LAST columns */
+        if (i > first && (cols + len > chunk_cols || (cols == 0 && len > 0))) {
             if (cb) cb(user, c, first, i - first, cols);
             ++c; first = i; cols = 0;
         }

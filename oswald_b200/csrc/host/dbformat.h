@@ -11,6 +11,7 @@
  *      bits 0-4  residue code 0..23
  *      bit  5    OSW_COL_FIRST  first column of a sequence (DP state restarts here)
  *      bit  6    OSW_COL_LAST   last column of a sequence (its score is complete here)
+ * Empty sequences form a chunk of their own without columns (their scores stay 0).
  * Chunk streams start on 128-byte boundaries (padding bytes are OSW_COL_PADBYTE), so a warp reads a
  * stream with coalesced 128-bit loads.
  *

@@ -194,6 +194,32 @@ def run_config(cfg, s, args, rng, queries_all):
 
 
 
+def reference_binary_matrix(s, queries_all, n_sample=20000):
+    """The reference binary itself (host AVX2 path) on a 20 000-sequence database with all 20
+    queries: every raw score it computes (dumped by the shim's sort_scores hook) against the GPU."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "oswald_ref")
+    if not os.path.exists(ref):
+        return {"config": "2-sample-vs-reference-binary", "skipped": "oracle/_ref/oswald_ref not built"}
+    db, _ = build_db(n_sample, bench.MU, 0.6, 777)
+    queries = ob.Queries.from_list(queries_all)
+    seqs = [db.sequence(i) for i in range(db.n_seqs)]
+    with tempfile.TemporaryDirectory() as tmp:
+        bench.write_fasta(os.path.join(tmp, "db.fasta"), seqs, "s")
+        bench.write_fasta(os.path.join(tmp, "q.fasta"), queries_all, "q")
+        subprocess.run([ref, "-O", "preprocess", "-i", "db.fasta", "-o", "db", "-c", "4"], cwd=tmp, check=True, capture_output=True)
+        env = dict(os.environ, OSWALD_ORACLE_DUMP=os.path.join(tmp, "dump.bin"))
+        t0 = time.time()
+        subprocess.run([ref, "-O", "search", "-q", "q.fasta", "-d", "db", "-m", "1", "-v", "32", "-c", str(os.cpu_count() or 1),
+                        "-p", "0.1", "-r", "10"], cwd=tmp, check=True, capture_output=True, env=env)
+        secs = time.time() - t0
+        want = np.fromfile(os.path.join(tmp, "dump.bin"), dtype=np.int32).reshape(queries.n, db.n_seqs)
+    s.load_db(db)
+    hits, tm, scores = s.search(queries, ob.matrix("blosum62"), 10, 2, top=10, all_scores=True)
+    return {"config": "2-sample-vs-reference-binary", "what": "every raw score of the reference binary (20 queries x %d sequences)" % db.n_seqs,
+            "pairs": int(want.size), "oracle_mismatches": int((scores != want).sum()),
+            "top_r_matches_reference_order": rank_rows(want, 10) == hits, "reference_wall_seconds": round(secs, 1)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,2,3,4,5")
@@ -211,6 +237,10 @@ def main():
             import traceback
             traceback.print_exc()
             r = {"config": cfg, "error": repr(e), "oracle_mismatches": 1}
+        results.append(r)
+        print(json.dumps(r), flush=True)
+    if 2 in todo:
+        r = reference_binary_matrix(s, queries_all)
         results.append(r)
         print(json.dumps(r), flush=True)
     s.close()

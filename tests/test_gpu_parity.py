@@ -273,3 +273,28 @@ def test_invalid_inputs_are_rejected(searcher):
         searcher.load_db(bad_db)
     searcher.load_db(db)                       # the context stays usable
     check(searcher, db, q, "blosum62", 10, 2, 5)
+
+
+def test_fuzz_small_cases(searcher):
+    """Randomised sweep: query counts and lengths (including empty queries and empty database
+    sequences), matrices, gap penalties, chunk sizes, top-r and all three first-stage modes."""
+    rng = np.random.default_rng(20261018)
+    names = ob.matrix_names()
+    for case in range(40):
+        n = int(rng.integers(1, 400))
+        lo, hi = (0, 8) if case % 7 == 0 else (1, int(rng.integers(5, 700)))
+        seqs = [rng.integers(0, 24, size=int(l)).astype(np.uint8) if case % 5 == 0 else AA[rng.integers(0, 20, size=int(l))]
+                for l in rng.integers(lo, hi + 1, size=n)]
+        nq = int(rng.integers(1, 7))
+        qlens = [int(rng.choice([0, 1, 7, 33, 150, 400, 1300, 2900])) if rng.random() < 0.5 else int(rng.integers(1, 600)) for _ in range(nq)]
+        qs = [AA[rng.integers(0, 20, size=m)] for m in qlens]
+        if len(seqs) > 3 and qlens[0] > 3:
+            seqs[2] = np.concatenate([qs[0][: qlens[0] // 2], seqs[2]])[:65535]
+        db = make_db(seqs)
+        q = ob.Queries.from_list(qs)
+        name = names[int(rng.integers(0, len(names)))]
+        go, ge = int(rng.integers(0, 30)), int(rng.integers(0, 6))
+        top = int(rng.choice([1, 3, 10, 50, n + 5]))
+        searcher.load_db(db, max_chunk_residues=int(rng.choice([0, 0, 32, 200, 1000])))
+        mode = list(MODES.values())[case % 3]
+        check(searcher, db, q, name, go, ge, top, mask=mode)
