@@ -24,10 +24,10 @@ build/%.o: oswald_b200/csrc/cuda/%.cu oswald_b200/csrc/cuda/osw_internal.h oswal
 
 build/%.o: oswald_b200/csrc/host/%.c $(wildcard oswald_b200/csrc/host/*.h) oswald_b200/csrc/host/submat_tri.inc
 	@mkdir -p build
-	$(HOSTCC) -O2 -fPIC -std=c11 -Wall -Iinclude -c $< -o $@
+	$(HOSTCC) -O2 -fPIC -std=c11 -Wall -fopenmp -Iinclude -c $< -o $@
 
 oswald_b200/liboswald_cuda.so: $(CUOBJ) build/dbformat.o build/submat.o
-	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart_static -lpthread -ldl -lrt
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart_static -lpthread -ldl -lrt -lgomp
 
 oswald_b200/oswald: $(CLISRC) oswald_b200/liboswald_cuda.so
 	$(HOSTCC) -O2 -std=gnu11 -Wall -fopenmp -Iinclude -Ioswald_b200/csrc/host -o $@ $(CLISRC) \

@@ -260,23 +260,32 @@ extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *
     for (int i = 0; i < c->n_dev; ++i) {
         DevState &d = c->devs[i];
         free_db(d);
-        const int brc = osw_shard_build(residues, offsets, n_seqs, (uint32_t)shard_rank * c->n_dev + i, n_shards, chunk_cols, &d.shard);
-        if (brc == -2) { snprintf(g_err, sizeof g_err, "the database holds a residue code outside 0..23"); return OSW_E_ARG; }
-        if (brc != 0) return OSW_E_NOMEM;
-        const osw_shard &s = d.shard;
+        // the two streams are built straight into pinned host memory (the source of every upload)
+        struct Pinned { uint8_t *ptr[2]; int n; } pinned = {{nullptr, nullptr}, 0};
+        auto pinned_alloc = [](size_t bytes, void *user) -> void * {
+            Pinned *pn = (Pinned *)user;
+            void *ptr = nullptr;
+            if (pn->n >= 2 || cudaMallocHost(&ptr, bytes) != cudaSuccess) return nullptr;
+            pn->ptr[pn->n++] = (uint8_t *)ptr;
+            return ptr;
+        };
         CK(cudaSetDevice(d.dev));
+        const int brc = osw_shard_build_ex(residues, offsets, n_seqs, (uint32_t)shard_rank * c->n_dev + i, n_shards, chunk_cols,
+                                           pinned_alloc, &pinned, &d.shard);
+        if (brc != 0) {
+            for (int k = 0; k < pinned.n; ++k) cudaFreeHost(pinned.ptr[k]);
+            if (brc == -2) { snprintf(g_err, sizeof g_err, "the database holds a residue code outside 0..23"); return OSW_E_ARG; }
+            return OSW_E_NOMEM;
+        }
+        d.h_stream = d.shard.stream; d.h_pair = d.shard.pair_stream;     // owned by DevState (freed in free_db)
+        d.shard.stream = nullptr; d.shard.pair_stream = nullptr;
+        const osw_shard &s = d.shard;
         CK(cudaMalloc(&d.d_stream, s.stream_bytes ? s.stream_bytes : 1));
         CK(cudaMalloc(&d.d_chunks, (s.n_chunks ? s.n_chunks : 1) * sizeof(osw_chunk)));
         CK(cudaMalloc(&d.d_canon, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint32_t)));
         CK(cudaMalloc(&d.d_seq_off, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint64_t)));
         CK(cudaMalloc(&d.d_seq_len, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint32_t)));
-        CK(cudaMallocHost(&d.h_stream, s.stream_bytes ? s.stream_bytes : 1));
-        memcpy(d.h_stream, s.stream, s.stream_bytes);
-        free(d.shard.stream); d.shard.stream = nullptr;      // the pinned copy is the one kept
         CK(cudaMalloc(&d.d_pair, s.pair_cols ? 2 * s.pair_cols : 1));
-        CK(cudaMallocHost(&d.h_pair, s.pair_cols ? 2 * s.pair_cols : 1));
-        memcpy(d.h_pair, s.pair_stream, 2 * s.pair_cols);
-        free(d.shard.pair_stream); d.shard.pair_stream = nullptr;
         int rc = upload_db(d);
         if (rc != OSW_OK) return rc;
         c->n_seqs_local += s.n_seqs; c->residues_local += s.n_residues; c->chunks_local += s.n_chunks;

@@ -1,7 +1,14 @@
-/* dbformat.c - see dbformat.h. */
+/* dbformat.c - see dbformat.h.
+ *
+ * Two steps: a serial walk over the sequence lengths that lays out this shard's chunks (offsets
+ * into both streams, first sequence), then a fill of the chunks, which are independent of each
+ * other (OpenMP).  The two big buffers can come from a caller-supplied allocator (the CUDA
+ * library passes pinned memory so that the streams are copied to the GPU straight from here). */
 #include "dbformat.h"
 #include <stdlib.h>
 #include <string.h>
+
+#define OSW_PAIR_ALIGN 64      /* columns */
 
 /* Walks the canonical sequence list and reports chunk boundaries through `cb`.
  * A chunk closes when adding the next sequence would pass chunk_cols (and it is non-empty). */
@@ -27,9 +34,6 @@ uint64_t osw_count_chunks(const uint64_t *offsets, uint64_t n_seqs, uint32_t chu
     return walk_chunks(offsets, n_seqs, chunk_cols, NULL, NULL);
 }
 
-#define OSW_PAIR_ALIGN 64      /* columns */
-typedef struct { uint32_t shard, n_shards; uint64_t seqs, cols, bytes, chunks, pair_cols; uint32_t max_len;
-                 const uint64_t *off; } tally_t;
 /* columns of a chunk in the pair stream: sum over pairs of the longer length (ascending order:
  * the second sequence of a pair, or the single last one) */
 static uint64_t pair_columns(const uint64_t *off, uint64_t first, uint64_t ns) {
@@ -40,94 +44,127 @@ static uint64_t pair_columns(const uint64_t *off, uint64_t first, uint64_t ns) {
     }
     return cols;
 }
+
+typedef struct { uint32_t shard, n_shards; uint64_t seqs, cols, bytes, chunks, pair_cols; uint32_t max_len;
+                 const uint64_t *off; } tally_t;
 static void tally_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t cols) {
     tally_t *t = (tally_t *)u;
+    (void)cols;
     if (c % t->n_shards != t->shard) return;
-    t->seqs += ns; t->cols += cols; t->chunks++;
-    t->bytes += (cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
-    t->pair_cols += (pair_columns(t->off, first, ns) + OSW_PAIR_ALIGN - 1) / OSW_PAIR_ALIGN * OSW_PAIR_ALIGN;
-    uint64_t last = t->off[first + ns] - t->off[first + ns - 1];   /* longest: order is ascending */
-    if (last > t->max_len) t->max_len = (uint32_t)last;
+    t->chunks++; t->seqs += ns;
 }
 
-typedef struct { uint32_t shard, n_shards; const uint8_t *res; const uint64_t *off; osw_shard *s;
-                 uint64_t seq_cursor, byte_cursor, pair_cursor; uint32_t chunk_cursor; int bad_residue; } fill_t;
-static void fill_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t cols) {
-    fill_t *f = (fill_t *)u;
-    if (c % f->n_shards != f->shard) return;
-    osw_shard *s = f->s;
-    /* chunks are stored in reverse so that index 0 is the longest-sequence chunk */
-    osw_chunk *ck = &s->chunks[s->n_chunks - 1 - f->chunk_cursor++];
-    ck->stream_off = f->byte_cursor; ck->n_cols = (uint32_t)cols; ck->n_seqs = (uint32_t)ns;
-    ck->seq0 = (uint32_t)f->seq_cursor; ck->canon0 = (uint32_t)first;
-    uint8_t *p = s->stream + f->byte_cursor;
-    for (uint64_t i = first; i < first + ns; ++i) {
-        uint64_t len = f->off[i + 1] - f->off[i];
-        const uint8_t *src = f->res + f->off[i];
-        uint64_t l = f->seq_cursor++;
+/* layout pass: directory entries in walk order (ascending length), offsets assigned in that order */
+typedef struct { uint32_t shard, n_shards; const uint64_t *off; osw_chunk *dir; uint64_t *first_seq;
+                 uint64_t n, seq_cursor, byte_cursor, pair_cursor, cols; uint32_t max_len; } layout_t;
+static void layout_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t cols) {
+    layout_t *l = (layout_t *)u;
+    if (c % l->n_shards != l->shard) return;
+    osw_chunk *ck = &l->dir[l->n];
+    l->first_seq[l->n] = first;
+    ck->stream_off = l->byte_cursor; ck->n_cols = (uint32_t)cols; ck->n_seqs = (uint32_t)ns;
+    ck->seq0 = (uint32_t)l->seq_cursor; ck->canon0 = (uint32_t)first;
+    ck->pair_off = l->pair_cursor; ck->n_pair_cols = (uint32_t)pair_columns(l->off, first, ns); ck->reserved = 0;
+    l->byte_cursor += (cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
+    l->pair_cursor += ((uint64_t)ck->n_pair_cols + OSW_PAIR_ALIGN - 1) / OSW_PAIR_ALIGN * OSW_PAIR_ALIGN;
+    l->seq_cursor += ns; l->cols += cols;
+    uint64_t last = l->off[first + ns] - l->off[first + ns - 1];   /* longest: order is ascending */
+    if (last > l->max_len) l->max_len = (uint32_t)last;
+    l->n++;
+}
+
+/* fills one chunk (both streams and the per-sequence tables); returns 1 if a residue code is invalid */
+static int fill_chunk(const uint8_t *res, const uint64_t *off, const osw_chunk *ck, uint64_t first, osw_shard *s) {
+    int bad = 0;
+    const uint64_t ns = ck->n_seqs;
+    uint8_t *p = s->stream + ck->stream_off;
+    for (uint64_t k = 0; k < ns; ++k) {
+        const uint64_t i = first + k, len = off[i + 1] - off[i];
+        const uint8_t *src = res + off[i];
+        const uint64_t l = ck->seq0 + k;
         s->canon[l] = (uint32_t)i; s->seq_off[l] = (uint64_t)(p - s->stream); s->seq_len[l] = (uint32_t)len;
-        for (uint64_t k = 0; k < len; ++k) {
-            if (src[k] > 23) f->bad_residue = 1;               /* codes are 0..23 (sequences.c:163-175) */
-            p[k] = (uint8_t)(src[k] & OSW_COL_CODE);
+        for (uint64_t j = 0; j < len; ++j) {
+            if (src[j] > 23) bad = 1;                           /* codes are 0..23 (sequences.c:163-175) */
+            p[j] = (uint8_t)(src[j] & OSW_COL_CODE);
         }
         if (len) { p[0] |= OSW_COL_FIRST; p[len - 1] |= OSW_COL_LAST; }
         p += len;
     }
-    uint64_t padded = (cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
-    memset(p, OSW_COL_PADBYTE, padded - cols);
-    f->byte_cursor += padded;
+    const uint64_t padded = ((uint64_t)ck->n_cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
+    memset(p, OSW_COL_PADBYTE, padded - ck->n_cols);
     /* pair stream of the same chunk */
-    ck->pair_off = f->pair_cursor; ck->reserved = 0;
-    uint8_t *q = s->pair_stream + 2 * f->pair_cursor;
-    uint64_t pc = 0;
+    uint8_t *q = s->pair_stream + 2 * ck->pair_off;
     for (uint64_t k = 0; k < ns; k += 2) {
         const uint64_t ia = first + k, ib = first + k + 1;
         const int has_b = k + 1 < ns;
-        const uint64_t la = f->off[ia + 1] - f->off[ia], lb = has_b ? f->off[ib + 1] - f->off[ib] : 0;
+        const uint64_t la = off[ia + 1] - off[ia], lb = has_b ? off[ib + 1] - off[ib] : 0;
         const uint64_t n = la > lb ? la : lb;
-        const uint8_t *a = f->res + f->off[ia], *b = has_b ? f->res + f->off[ib] : NULL;
+        const uint8_t *a = res + off[ia], *b = has_b ? res + off[ib] : NULL;
         for (uint64_t j = 0; j < n; ++j) {
             q[2 * j] = (uint8_t)(j < la ? (a[j] & OSW_COL_CODE) : OSW_COL_PADBYTE);
             q[2 * j + 1] = (uint8_t)(j < lb ? (b[j] & OSW_COL_CODE) : OSW_COL_PADBYTE);
         }
         if (n) { q[0] |= OSW_COL_FIRST; q[2 * (n - 1)] |= OSW_COL_LAST; }
-        q += 2 * n; pc += n;
+        q += 2 * n;
     }
-    ck->n_pair_cols = (uint32_t)pc;
-    const uint64_t pc_padded = (pc + OSW_PAIR_ALIGN - 1) / OSW_PAIR_ALIGN * OSW_PAIR_ALIGN;
-    memset(q, OSW_COL_PADBYTE, 2 * (pc_padded - pc));
-    f->pair_cursor += pc_padded;
+    const uint64_t pc_padded = ((uint64_t)ck->n_pair_cols + OSW_PAIR_ALIGN - 1) / OSW_PAIR_ALIGN * OSW_PAIR_ALIGN;
+    memset(q, OSW_COL_PADBYTE, 2 * (pc_padded - ck->n_pair_cols));
+    return bad;
 }
 
-int osw_shard_build(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
-                    uint32_t shard, uint32_t n_shards, uint32_t chunk_cols, osw_shard *out) {
+int osw_shard_build_ex(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
+                       uint32_t shard, uint32_t n_shards, uint32_t chunk_cols,
+                       osw_alloc_fn alloc, void *alloc_user, osw_shard *out) {
     if (!out || !n_shards || shard >= n_shards || (n_seqs && (!residues || !offsets))) return -1;
     if (!chunk_cols) chunk_cols = OSW_CHUNK_COLS_DEFAULT;
     memset(out, 0, sizeof *out);
     tally_t t; memset(&t, 0, sizeof t);
     t.shard = shard; t.n_shards = n_shards; t.off = offsets;
     walk_chunks(offsets, n_seqs, chunk_cols, tally_cb, &t);
-    out->n_seqs = t.seqs; out->n_residues = t.cols; out->stream_bytes = t.bytes;
-    out->n_chunks = (uint32_t)t.chunks; out->max_len = t.max_len;
-    out->pair_cols = t.pair_cols;
-    out->stream  = (uint8_t *)malloc(t.bytes ? t.bytes : 1);
-    out->pair_stream = (uint8_t *)malloc(t.pair_cols ? 2 * t.pair_cols : 1);
-    out->chunks  = (osw_chunk *)malloc((t.chunks ? t.chunks : 1) * sizeof(osw_chunk));
-    out->canon   = (uint32_t *)malloc((t.seqs ? t.seqs : 1) * sizeof(uint32_t));
-    out->seq_off = (uint64_t *)malloc((t.seqs ? t.seqs : 1) * sizeof(uint64_t));
-    out->seq_len = (uint32_t *)malloc((t.seqs ? t.seqs : 1) * sizeof(uint32_t));
-    if (!out->stream || !out->pair_stream || !out->chunks || !out->canon || !out->seq_off || !out->seq_len) {
-        osw_shard_free(out); return -1;
+    osw_chunk *dir = (osw_chunk *)malloc((t.chunks ? t.chunks : 1) * sizeof(osw_chunk));
+    uint64_t *first_seq = (uint64_t *)malloc((t.chunks ? t.chunks : 1) * sizeof(uint64_t));
+    if (!dir || !first_seq) { free(dir); free(first_seq); return -1; }
+    layout_t l; memset(&l, 0, sizeof l);
+    l.shard = shard; l.n_shards = n_shards; l.off = offsets; l.dir = dir; l.first_seq = first_seq;
+    walk_chunks(offsets, n_seqs, chunk_cols, layout_cb, &l);
+    out->n_seqs = l.seq_cursor; out->n_residues = l.cols; out->stream_bytes = l.byte_cursor;
+    out->pair_cols = l.pair_cursor; out->n_chunks = (uint32_t)l.n; out->max_len = l.max_len;
+    out->external_streams = alloc != NULL;
+    if (alloc) {
+        out->stream = (uint8_t *)alloc(out->stream_bytes ? out->stream_bytes : 1, alloc_user);
+        out->pair_stream = (uint8_t *)alloc(out->pair_cols ? 2 * out->pair_cols : 1, alloc_user);
+    } else {
+        out->stream = (uint8_t *)malloc(out->stream_bytes ? out->stream_bytes : 1);
+        out->pair_stream = (uint8_t *)malloc(out->pair_cols ? 2 * out->pair_cols : 1);
     }
-    fill_t f; memset(&f, 0, sizeof f);
-    f.shard = shard; f.n_shards = n_shards; f.res = residues; f.off = offsets; f.s = out;
-    walk_chunks(offsets, n_seqs, chunk_cols, fill_cb, &f);
-    if (f.bad_residue) { osw_shard_free(out); return -2; }
+    out->chunks  = (osw_chunk *)malloc((l.n ? l.n : 1) * sizeof(osw_chunk));
+    out->canon   = (uint32_t *)malloc((out->n_seqs ? out->n_seqs : 1) * sizeof(uint32_t));
+    out->seq_off = (uint64_t *)malloc((out->n_seqs ? out->n_seqs : 1) * sizeof(uint64_t));
+    out->seq_len = (uint32_t *)malloc((out->n_seqs ? out->n_seqs : 1) * sizeof(uint32_t));
+    if (!out->stream || !out->pair_stream || !out->chunks || !out->canon || !out->seq_off || !out->seq_len) {
+        free(dir); free(first_seq);
+        osw_shard_free(out);
+        return -1;
+    }
+    int bad = 0;
+    const long long n_chunks = (long long)l.n;
+#pragma omp parallel for schedule(dynamic, 64) reduction(| : bad)
+    for (long long k = 0; k < n_chunks; ++k) bad |= fill_chunk(residues, offsets, &dir[k], first_seq[k], out);
+    /* the directory is stored in reverse so that index 0 is the longest-sequence chunk */
+    for (uint64_t k = 0; k < l.n; ++k) out->chunks[l.n - 1 - k] = dir[k];
+    free(dir); free(first_seq);
+    if (bad) { osw_shard_free(out); return -2; }
     return 0;
+}
+
+int osw_shard_build(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
+                    uint32_t shard, uint32_t n_shards, uint32_t chunk_cols, osw_shard *out) {
+    return osw_shard_build_ex(residues, offsets, n_seqs, shard, n_shards, chunk_cols, NULL, NULL, out);
 }
 
 void osw_shard_free(osw_shard *s) {
     if (!s) return;
-    free(s->stream); free(s->pair_stream); free(s->chunks); free(s->canon); free(s->seq_off); free(s->seq_len);
+    if (!s->external_streams) { free(s->stream); free(s->pair_stream); }   /* external ones belong to the allocator's owner */
+    free(s->chunks); free(s->canon); free(s->seq_off); free(s->seq_len);
     memset(s, 0, sizeof *s);
 }

@@ -58,6 +58,7 @@ typedef struct osw_shard {
     uint64_t   stream_bytes;   /* size of stream (multiple of OSW_CHUNK_ALIGN) */
     uint32_t   n_chunks;
     uint32_t   max_len;        /* longest sequence in the shard */
+    int        external_streams; /* stream / pair_stream came from a caller's allocator: not freed here */
     uint8_t   *stream;         /* column stream, chunks back to back */
     uint64_t   pair_cols;      /* columns of the pair stream (multiple of 64) */
     uint8_t   *pair_stream;    /* 2 * pair_cols bytes */
@@ -74,6 +75,12 @@ uint64_t osw_count_chunks(const uint64_t *offsets, uint64_t n_seqs, uint32_t chu
  * Returns 0, -1 on allocation failure / bad arguments, -2 if a residue code is not in 0..23. */
 int osw_shard_build(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
                     uint32_t shard, uint32_t n_shards, uint32_t chunk_cols, osw_shard *out);
+/* Same, with the two stream buffers taken from `alloc(bytes, user)` (e.g. pinned host memory);
+ * such buffers are not freed by osw_shard_free. */
+typedef void *(*osw_alloc_fn)(size_t bytes, void *user);
+int osw_shard_build_ex(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
+                       uint32_t shard, uint32_t n_shards, uint32_t chunk_cols,
+                       osw_alloc_fn alloc, void *alloc_user, osw_shard *out);
 void osw_shard_free(osw_shard *s);
 
 #ifdef __cplusplus

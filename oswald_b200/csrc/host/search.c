@@ -8,6 +8,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <sys/time.h>
+
+static double wall_s(void) { struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + tv.tv_usec * 1e-6; }
+#define PHASE(name) do { if (trace) { double t_ = wall_s(); fprintf(stderr, "oswald trace: %-28s %.3f s\n", name, t_ - t_phase); t_phase = t_; } } while (0)
 
 int gpu_info(void) {
     int n = 0;
@@ -19,6 +23,8 @@ int gpu_info(void) {
 }
 
 int gpu_search(const osw_options *opt) {
+    const int trace = getenv("OSW_TRACE") != NULL;
+    double t_phase = wall_s();
     printf("\nOSWALD v%s \n\n", OSWALD_VERSION);
     printf("Database file:\t\t\t%s\n", opt->sequences_filename);
 
@@ -42,8 +48,10 @@ int gpu_search(const osw_options *opt) {
     }
     a_disp[nq] = (uint32_t)Q;
 
+    PHASE("load queries");
     osw_database db;
     if ((rc = load_database(opt->sequences_filename, &db)) != 0) return rc;
+    PHASE("map database");
     printf("Database size:\t\t\t%ld sequences (%ld residues) \n", (long)db.n_seqs, (long)db.n_residues);
     printf("Longest database sequence: \t%d residues\n", (int)db.max_len);
     printf("Substitution matrix:\t\t%s\n", opt->submat_name);
@@ -60,11 +68,13 @@ int gpu_search(const osw_options *opt) {
         printf("OSWALD: cannot initialise %u GPU(s): %s (%s).\n", opt->num_devices, osw_strerror(rc), osw_last_error());
         return 1;
     }
+    PHASE("osw_init");
     if ((rc = osw_db_load(ctx, db.residues, db.offsets, db.n_seqs, 0, 1, opt->max_chunk_size)) != OSW_OK) {
         printf("OSWALD: cannot load the database on the GPU(s): %s (%s).\n", osw_strerror(rc), osw_last_error());
         osw_free(ctx);
         return 1;
     }
+    PHASE("osw_db_load (layout + H2D)");
     osw_hit *hits = (osw_hit *)malloc(((size_t)nq * (top ? top : 1)) * sizeof(osw_hit));
     uint32_t *n_hits = (uint32_t *)calloc((size_t)nq, sizeof(uint32_t));
     int32_t *all = NULL;
@@ -77,6 +87,7 @@ int gpu_search(const osw_options *opt) {
         osw_free(ctx);
         return 1;
     }
+    PHASE("osw_search");
     if (opt->dump_scores) {
         FILE *f = fopen(opt->dump_scores, "wb");
         if (!f) { printf("OSWALD: cannot write %s.\n", opt->dump_scores); return 2; }
@@ -90,6 +101,7 @@ int gpu_search(const osw_options *opt) {
     for (size_t k = 0; k < n_print; ++k) idx[k] = hits[k].index;
     if ((rc = load_database_headers(opt->sequences_filename, idx, n_print, titles)) != 0) return rc;
 
+    PHASE("load titles of the hits");
     for (int i = 0; i < nq; ++i) {                     /* report: HybridSearch.c:1213-1224 */
         printf("\nQuery no.\t\t\t%d\n", i + 1);
         printf("Query description: \t\t%s\n", qf.titles[qperm[i]]);

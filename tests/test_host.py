@@ -44,7 +44,8 @@ class Chunk(C.Structure):
 
 class Shard(C.Structure):
     _fields_ = [("n_seqs", C.c_uint64), ("n_residues", C.c_uint64), ("stream_bytes", C.c_uint64),
-                ("n_chunks", C.c_uint32), ("max_len", C.c_uint32), ("stream", C.POINTER(C.c_uint8)),
+                ("n_chunks", C.c_uint32), ("max_len", C.c_uint32), ("external_streams", C.c_int),
+                ("stream", C.POINTER(C.c_uint8)),
                 ("pair_cols", C.c_uint64), ("pair_stream", C.POINTER(C.c_uint8)),
                 ("chunks", C.POINTER(Chunk)), ("canon", C.POINTER(C.c_uint32)),
                 ("seq_off", C.POINTER(C.c_uint64)), ("seq_len", C.POINTER(C.c_uint32))]
