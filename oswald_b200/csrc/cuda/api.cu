@@ -98,7 +98,7 @@ int upload_db(DevState &d) {
     const osw_shard &s = d.shard;
     CK(cudaSetDevice(d.dev));
     CK(cudaMemcpyAsync(d.d_stream, d.h_stream, s.stream_bytes, cudaMemcpyHostToDevice, d.st));
-    CK(cudaMemcpyAsync(d.d_pair, d.h_pair, 2 * s.pair_cols, cudaMemcpyHostToDevice, d.st));
+    if (d.h_pair) CK(cudaMemcpyAsync(d.d_pair, d.h_pair, 2 * s.pair_cols, cudaMemcpyHostToDevice, d.st));
     CK(cudaMemcpyAsync(d.d_chunks, s.chunks, s.n_chunks * sizeof(osw_chunk), cudaMemcpyHostToDevice, d.st));
     CK(cudaMemcpyAsync(d.d_canon, s.canon, s.n_seqs * sizeof(uint32_t), cudaMemcpyHostToDevice, d.st));
     CK(cudaMemcpyAsync(d.d_seq_off, s.seq_off, s.n_seqs * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st));
@@ -271,7 +271,7 @@ extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *
         };
         CK(cudaSetDevice(d.dev));
         const int brc = osw_shard_build_ex(residues, offsets, n_seqs, (uint32_t)shard_rank * c->n_dev + i, n_shards, chunk_cols,
-                                           pinned_alloc, &pinned, &d.shard);
+                                           0 /* the pair stream is made when a search first needs it */, pinned_alloc, &pinned, &d.shard);
         if (brc != 0) {
             for (int k = 0; k < pinned.n; ++k) cudaFreeHost(pinned.ptr[k]);
             if (brc == -2) { snprintf(g_err, sizeof g_err, "the database holds a residue code outside 0..23"); return OSW_E_ARG; }
@@ -285,7 +285,6 @@ extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *
         CK(cudaMalloc(&d.d_canon, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint32_t)));
         CK(cudaMalloc(&d.d_seq_off, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint64_t)));
         CK(cudaMalloc(&d.d_seq_len, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint32_t)));
-        CK(cudaMalloc(&d.d_pair, s.pair_cols ? 2 * s.pair_cols : 1));
         int rc = upload_db(d);
         if (rc != OSW_OK) return rc;
         c->n_seqs_local += s.n_seqs; c->residues_local += s.n_residues; c->chunks_local += s.n_chunks;
@@ -306,7 +305,7 @@ extern "C" int osw_db_upload(osw_ctx *c, uint64_t *bytes) {
         int rc = upload_db(c->devs[i]);
         if (rc != OSW_OK) return rc;
         const osw_shard &s = c->devs[i].shard;
-        total += s.stream_bytes + 2 * s.pair_cols + s.n_chunks * sizeof(osw_chunk) + s.n_seqs * (sizeof(uint32_t) * 2 + sizeof(uint64_t));
+        total += s.stream_bytes + (c->devs[i].h_pair ? 2 * s.pair_cols : 0) + s.n_chunks * sizeof(osw_chunk) + s.n_seqs * (sizeof(uint32_t) * 2 + sizeof(uint64_t));
     }
     for (int i = 0; i < c->n_dev; ++i) {
         CK(cudaSetDevice(c->devs[i].dev));
@@ -407,6 +406,13 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
 
     uint32_t slot = 0;
     d.trace.clear();
+    if (use_u16 && N && !passes.empty() && passes[0].pair_db && !d.h_pair) {
+        // first pair-database search on this database: derive the pair stream from the plain one
+        CK(cudaMallocHost(&d.h_pair, s.pair_cols ? 2 * s.pair_cols : 1));
+        osw_shard_fill_pair(&s, d.h_stream, d.h_pair);
+        CK(cudaMalloc(&d.d_pair, s.pair_cols ? 2 * s.pair_cols : 1));
+        CK(cudaMemcpyAsync(d.d_pair, d.h_pair, 2 * s.pair_cols, cudaMemcpyHostToDevice, d.st));
+    }
     if (use_u16 && N) {
         auto launch = [&](const OswPass &ps, uint32_t first, uint32_t end, cudaStream_t st) -> int {
             if (slot >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }

@@ -74,7 +74,7 @@ static void layout_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t
 }
 
 /* fills one chunk (both streams and the per-sequence tables); returns 1 if a residue code is invalid */
-static int fill_chunk(const uint8_t *res, const uint64_t *off, const osw_chunk *ck, uint64_t first, osw_shard *s) {
+static int fill_chunk(const uint8_t *res, const uint64_t *off, const osw_chunk *ck, uint64_t first, osw_shard *s, int with_pair) {
     int bad = 0;
     const uint64_t ns = ck->n_seqs;
     uint8_t *p = s->stream + ck->stream_off;
@@ -92,6 +92,7 @@ static int fill_chunk(const uint8_t *res, const uint64_t *off, const osw_chunk *
     }
     const uint64_t padded = ((uint64_t)ck->n_cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
     memset(p, OSW_COL_PADBYTE, padded - ck->n_cols);
+    if (!with_pair) return bad;
     /* pair stream of the same chunk */
     uint8_t *q = s->pair_stream + 2 * ck->pair_off;
     for (uint64_t k = 0; k < ns; k += 2) {
@@ -113,7 +114,7 @@ static int fill_chunk(const uint8_t *res, const uint64_t *off, const osw_chunk *
 }
 
 int osw_shard_build_ex(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
-                       uint32_t shard, uint32_t n_shards, uint32_t chunk_cols,
+                       uint32_t shard, uint32_t n_shards, uint32_t chunk_cols, int with_pair,
                        osw_alloc_fn alloc, void *alloc_user, osw_shard *out) {
     if (!out || !n_shards || shard >= n_shards || (n_seqs && (!residues || !offsets))) return -1;
     if (!chunk_cols) chunk_cols = OSW_CHUNK_COLS_DEFAULT;
@@ -132,16 +133,16 @@ int osw_shard_build_ex(const uint8_t *residues, const uint64_t *offsets, uint64_
     out->external_streams = alloc != NULL;
     if (alloc) {
         out->stream = (uint8_t *)alloc(out->stream_bytes ? out->stream_bytes : 1, alloc_user);
-        out->pair_stream = (uint8_t *)alloc(out->pair_cols ? 2 * out->pair_cols : 1, alloc_user);
+        if (with_pair) out->pair_stream = (uint8_t *)alloc(out->pair_cols ? 2 * out->pair_cols : 1, alloc_user);
     } else {
         out->stream = (uint8_t *)malloc(out->stream_bytes ? out->stream_bytes : 1);
-        out->pair_stream = (uint8_t *)malloc(out->pair_cols ? 2 * out->pair_cols : 1);
+        if (with_pair) out->pair_stream = (uint8_t *)malloc(out->pair_cols ? 2 * out->pair_cols : 1);
     }
     out->chunks  = (osw_chunk *)malloc((l.n ? l.n : 1) * sizeof(osw_chunk));
     out->canon   = (uint32_t *)malloc((out->n_seqs ? out->n_seqs : 1) * sizeof(uint32_t));
     out->seq_off = (uint64_t *)malloc((out->n_seqs ? out->n_seqs : 1) * sizeof(uint64_t));
     out->seq_len = (uint32_t *)malloc((out->n_seqs ? out->n_seqs : 1) * sizeof(uint32_t));
-    if (!out->stream || !out->pair_stream || !out->chunks || !out->canon || !out->seq_off || !out->seq_len) {
+    if (!out->stream || (with_pair && !out->pair_stream) || !out->chunks || !out->canon || !out->seq_off || !out->seq_len) {
         free(dir); free(first_seq);
         osw_shard_free(out);
         return -1;
@@ -149,7 +150,7 @@ int osw_shard_build_ex(const uint8_t *residues, const uint64_t *offsets, uint64_
     int bad = 0;
     const long long n_chunks = (long long)l.n;
 #pragma omp parallel for schedule(dynamic, 64) reduction(| : bad)
-    for (long long k = 0; k < n_chunks; ++k) bad |= fill_chunk(residues, offsets, &dir[k], first_seq[k], out);
+    for (long long k = 0; k < n_chunks; ++k) bad |= fill_chunk(residues, offsets, &dir[k], first_seq[k], out, with_pair);
     /* the directory is stored in reverse so that index 0 is the longest-sequence chunk */
     for (uint64_t k = 0; k < l.n; ++k) out->chunks[l.n - 1 - k] = dir[k];
     free(dir); free(first_seq);
@@ -159,7 +160,34 @@ int osw_shard_build_ex(const uint8_t *residues, const uint64_t *offsets, uint64_
 
 int osw_shard_build(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
                     uint32_t shard, uint32_t n_shards, uint32_t chunk_cols, osw_shard *out) {
-    return osw_shard_build_ex(residues, offsets, n_seqs, shard, n_shards, chunk_cols, NULL, NULL, out);
+    return osw_shard_build_ex(residues, offsets, n_seqs, shard, n_shards, chunk_cols, 1, NULL, NULL, out);
+}
+
+/* Pair stream from the plain one (same residues, flags stripped): used when the pair stream is
+ * first needed after the caller's database arrays are gone. */
+void osw_shard_fill_pair(const osw_shard *s, const uint8_t *stream, uint8_t *pair) {
+    const long long n_chunks = (long long)s->n_chunks;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long c = 0; c < n_chunks; ++c) {
+        const osw_chunk *ck = &s->chunks[c];
+        uint8_t *q = pair + 2 * ck->pair_off;
+        for (uint32_t k = 0; k < ck->n_seqs; k += 2) {
+            const uint64_t la = s->seq_len[ck->seq0 + k];
+            const int has_b = k + 1 < ck->n_seqs;
+            const uint64_t lb = has_b ? s->seq_len[ck->seq0 + k + 1] : 0;
+            const uint8_t *a = stream + s->seq_off[ck->seq0 + k];
+            const uint8_t *b = has_b ? stream + s->seq_off[ck->seq0 + k + 1] : NULL;
+            const uint64_t n = la > lb ? la : lb;
+            for (uint64_t j = 0; j < n; ++j) {
+                q[2 * j] = (uint8_t)(j < la ? (a[j] & OSW_COL_CODE) : OSW_COL_PADBYTE);
+                q[2 * j + 1] = (uint8_t)(j < lb ? (b[j] & OSW_COL_CODE) : OSW_COL_PADBYTE);
+            }
+            if (n) { q[0] |= OSW_COL_FIRST; q[2 * (n - 1)] |= OSW_COL_LAST; }
+            q += 2 * n;
+        }
+        const uint64_t pc_padded = ((uint64_t)ck->n_pair_cols + OSW_PAIR_ALIGN - 1) / OSW_PAIR_ALIGN * OSW_PAIR_ALIGN;
+        memset(q, OSW_COL_PADBYTE, 2 * (pc_padded - ck->n_pair_cols));
+    }
 }
 
 void osw_shard_free(osw_shard *s) {

@@ -79,8 +79,10 @@ int osw_shard_build(const uint8_t *residues, const uint64_t *offsets, uint64_t n
  * such buffers are not freed by osw_shard_free. */
 typedef void *(*osw_alloc_fn)(size_t bytes, void *user);
 int osw_shard_build_ex(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
-                       uint32_t shard, uint32_t n_shards, uint32_t chunk_cols,
+                       uint32_t shard, uint32_t n_shards, uint32_t chunk_cols, int with_pair,
                        osw_alloc_fn alloc, void *alloc_user, osw_shard *out);
+/* Fills pair[2 * s->pair_cols] from the shard's plain stream (for a deferred pair stream). */
+void osw_shard_fill_pair(const osw_shard *s, const uint8_t *stream, uint8_t *pair);
 void osw_shard_free(osw_shard *s);
 
 #ifdef __cplusplus
