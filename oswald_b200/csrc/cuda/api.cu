@@ -48,6 +48,7 @@ struct DevState {
     int8_t *d_matrix = nullptr;
     int2 *d_scratch = nullptr; size_t scratch_cap = 0;
     uint2 *d_bound = nullptr;                  // bottom rows handed from pass to pass (in place)
+    unsigned char *d_profile[2] = {nullptr, nullptr};   // profile table images, one per stream
     uint2 *d_pairs = nullptr; uint32_t pairs_cap = 0;
     uint32_t *d_counters = nullptr;            // [0] flagged count, [1..] chunk counters per launch
     unsigned long long *d_task_counter = nullptr;   // [0] i32 queue, [1] n_tasks mirror
@@ -196,6 +197,8 @@ extern "C" int osw_init(int n_devices, const int *devices, osw_ctx **out) {
             osw_free(c); return cuda_fail(e, "stream setup", __LINE__);
         }
         if ((e = cudaMalloc(&d.d_matrix, 24 * 32)) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_profile[0], OSW_PROFILE_BYTES)) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_profile[1], OSW_PROFILE_BYTES)) != cudaSuccess ||
             (e = cudaMalloc(&d.d_counters, (1 + MAX_LAUNCH_SLOTS) * sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_task_counter, 2 * sizeof(unsigned long long))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_cycles, MAX_LAUNCH_SLOTS * sizeof(unsigned long long))) != cudaSuccess ||
@@ -217,6 +220,7 @@ extern "C" void osw_free(osw_ctx *c) {
         if (d.st) cudaStreamSynchronize(d.st);
         free_db(d);
         cudaFree(d.d_scores); cudaFree(d.d_queries); cudaFree(d.d_qoff); cudaFree(d.d_matrix); cudaFree(d.d_scratch);
+        cudaFree(d.d_profile[0]); cudaFree(d.d_profile[1]);
         cudaFree(d.d_pairs); cudaFree(d.d_counters); cudaFree(d.d_task_counter); cudaFree(d.d_cycles);
         cudaFree(d.topr.hist); cudaFree(d.topr.prefix); cudaFree(d.topr.remaining); cudaFree(d.topr.out_count); cudaFree(d.topr.out_keys);
         if (d.h_keys) cudaFreeHost(d.h_keys);
@@ -420,6 +424,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             up.stream = d.d_stream; up.pair_stream = d.d_pair; up.chunks = d.d_chunks;
             up.chunk_first = first; up.chunk_end = end;
             up.queries = d.d_queries; up.q_off = d.d_qoff; up.matrix = d.d_matrix;
+            up.profile = d.d_profile[st == d.st2 ? 1 : 0];
             up.scores = d.d_scores; up.n_seqs = N;
             up.bound = d.d_bound;
             up.gap_open_extend = go + ge; up.gap_extend = ge;
@@ -431,7 +436,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             if (first == 0 && end == s.n_chunks) cols = ps.pair_db ? s.pair_cols : s.n_residues;
             else for (uint32_t k = first; k < end; ++k) cols += ps.pair_db ? s.chunks[k].n_pair_cols : s.chunks[k].n_cols;
             d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols});
-            ++slot; ++*launches;
+            ++slot; *launches += 2;               // profile_build_kernel + sw_u16_kernel
             *padded_cells += (uint64_t)ps.G * ps.R * 2 * cols;
             return OSW_OK;
         };

@@ -34,6 +34,7 @@ int  osw_i32_block_threads();
 // packed words.  The rows of a half are a stretch of that half's TRACK: the queries assigned
 // to the half, laid end to end with every query starting on a lane boundary.  A lane therefore
 // belongs to exactly one query per half.
+#define OSW_PROFILE_BYTES (232u * 1024u)   // room for the largest profile image
 #define OSW_LANE_START 1u    // the lane holds the query's first row: its input from above is "no row" (zeros)
 #define OSW_LANE_EMIT  2u    // the lane is the last one of its query in this pass: it publishes the maximum
 struct OswLaneDesc {
@@ -65,6 +66,7 @@ struct U16Params {
     const uint8_t   *queries;    // all queries back to back (codes)
     const uint32_t  *q_off;      // [nq+1]
     const int8_t    *matrix;
+    unsigned char   *profile;    // global image of the pass's profile table (>= OSW_PROFILE_BYTES), private to the stream
     int32_t         *scores;     // [nq][n_seqs]
     uint64_t         n_seqs;
     uint2           *bound;      // [max(stream_bytes, pair_cols)] (H,F) bottom row handed from pass to pass, in place; or nullptr

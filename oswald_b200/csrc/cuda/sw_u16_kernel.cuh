@@ -107,6 +107,74 @@ struct KArgs {
     uint32_t bias;           // B
 };
 
+// One 16-byte profile entry (4 rows x one residue) - and its high-half twin in pair-database mode -
+// written at its place in a table image starting at `base` (shared or global memory).
+template <int G, int R, bool PD>
+__device__ __forceinline__ void profile_entry(int idx, const KArgs &a, const int *s_mat, unsigned char *base) {
+    constexpr int P = pitch_quads(R);
+    constexpr int PITCH_B = prof_quads(G, R) * 16;
+    constexpr int COPY_B = (int)prof_copy_bytes(G, R);
+    constexpr int TABLE_B = COPY_B * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0);
+    const U16Params &p = a.p;
+    const int copy = idx / (24 * prof_quads(G, R));
+    const int rem = idx % (24 * prof_quads(G, R));
+    const int b = rem / prof_quads(G, R), slot = rem % prof_quads(G, R);
+    const int tt = slot / P, k = slot % P;
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (tt < G && k < R / 4) {
+        const OswLaneDesc da = a.lane[0][tt], db = a.lane[1][tt];
+        const uint8_t *qa = da.q_len ? p.queries + p.q_off[da.query] : p.queries;
+        const uint8_t *qb = db.q_len ? p.queries + p.q_off[db.query] : p.queries;
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t ra = da.row0 + 4 * k + r, rb = db.row0 + 4 * k + r;
+            const int ca = ra < da.q_len ? qa[ra] : OSW_PAD_CODE;
+            const int cb = rb < db.q_len ? qb[rb] : OSW_PAD_CODE;
+            if (PD) w[r] = (uint32_t)s_mat[ca * 32 + b];            // track 0 only; split into halves below
+            else w[r] = ((uint32_t)s_mat[ca * 32 + b] & 0xffffu) | ((uint32_t)s_mat[cb * 32 + b] << 16);
+        }
+    }
+    // the second copy (G == 4) sits 64 bytes further modulo 128, i.e. 4 bank groups away
+    unsigned char *dst = base + copy * (COPY_B + 64) + b * PITCH_B + slot * 16;
+    if (PD) {
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0] & 0xffffu, w[1] & 0xffffu, w[2] & 0xffffu, w[3] & 0xffffu);
+        *reinterpret_cast<uint4 *>(dst + TABLE_B) = make_uint4(w[0] << 16, w[1] << 16, w[2] << 16, w[3] << 16);
+    } else {
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// Builds the pass's profile table image once, in global memory; every CTA of the scoring kernel
+// then brings it into shared memory with TMA bulk copies (cp.async.bulk + mbarrier).
+template <int G, int R, bool PD>
+__global__ void __launch_bounds__(256) profile_build_kernel(const KArgs a) {
+    __shared__ int s_mat[24 * 32];
+    for (int i = threadIdx.x; i < 24 * 32; i += 256) s_mat[i] = a.p.matrix[i];
+    __syncthreads();
+    const int n = prof_copies(G) * 24 * prof_quads(G, R);
+    for (int idx = blockIdx.x * 256 + threadIdx.x; idx < n; idx += gridDim.x * 256)
+        profile_entry<G, R, PD>(idx, a, s_mat, a.p.profile);
+}
+
+// ---- TMA bulk copy global -> shared, completion on an mbarrier --------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    }
+}
+
 // PD = "pair database" mode: both halves work on the SAME query rows (track 0) against two
 // different database sequences zipped in the pair stream; the score word of a row is the sum of a
 // low-half table entry (first sequence's residue) and a high-half table entry (second one's).
@@ -129,7 +197,6 @@ sw_u16_kernel(const KArgs a) {
     uint4 *s_mail = reinterpret_cast<uint4 *>(smem + PROF_B);
     uint4 *s_ring = s_mail + WARPS * 32;
     uint2 *s_oring = reinterpret_cast<uint2 *>(s_ring + WARPS * GROUPS * RING);     // [WARPS][32] bottom rows of the last 32 steps
-    __shared__ int s_mat[24 * 32];
     __shared__ uint32_t s_chunk[WARPS];
 
     const U16Params &p = a.p;
@@ -137,37 +204,22 @@ sw_u16_kernel(const KArgs a) {
     const int t = lane % G, grp = lane / G;
     long long clk0 = clock64();
 
-    // ---- build the pair profile for rows row0 .. row0+G*R-1 ------------------------------
-    for (int i = threadIdx.x; i < 24 * 32; i += THREADS) s_mat[i] = p.matrix[i];
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < prof_copies(G) * 24 * prof_quads(G, R); idx += THREADS) {
-        const int copy = idx / (24 * prof_quads(G, R));
-        const int rem = idx % (24 * prof_quads(G, R));
-        const int b = rem / prof_quads(G, R), slot = rem % prof_quads(G, R);
-        const int tt = slot / P, k = slot % P;
-        uint32_t w[4] = {0, 0, 0, 0};
-        if (tt < G && k < R / 4) {
-            const OswLaneDesc da = a.lane[0][tt], db = a.lane[1][tt];
-            const uint8_t *qa = da.q_len ? p.queries + p.q_off[da.query] : p.queries;
-            const uint8_t *qb = db.q_len ? p.queries + p.q_off[db.query] : p.queries;
-            for (int r = 0; r < 4; ++r) {
-                const uint32_t ra = da.row0 + 4 * k + r, rb = db.row0 + 4 * k + r;
-                const int ca = ra < da.q_len ? qa[ra] : OSW_PAD_CODE;
-                const int cb = rb < db.q_len ? qb[rb] : OSW_PAD_CODE;
-                if (PD) w[r] = (uint32_t)s_mat[ca * 32 + b];            // track 0 only; split into halves below
-                else w[r] = ((uint32_t)s_mat[ca * 32 + b] & 0xffffu) | ((uint32_t)s_mat[cb * 32 + b] << 16);
+    // ---- the pass's profile table (built once by profile_build_kernel): TMA bulk copies into shared memory
+    __shared__ __align__(8) unsigned long long s_mbar;
+    {
+        const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+        if (threadIdx.x == 0) mbar_init(mbar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(mbar, (uint32_t)PROF_B);
+            constexpr uint32_t PIECE = 32768;
+            for (uint32_t off = 0; off < (uint32_t)PROF_B; off += PIECE) {
+                const uint32_t n = (uint32_t)PROF_B - off < PIECE ? (uint32_t)PROF_B - off : PIECE;
+                bulk_g2s((uint32_t)__cvta_generic_to_shared(s_prof) + off, p.profile + off, n, mbar);
             }
         }
-        // the second copy (G == 4) sits 64 bytes further modulo 128, i.e. 4 bank groups away
-        unsigned char *dst = s_prof + copy * (COPY_B + 64) + b * PITCH_B + slot * 16;
-        if (PD) {
-            *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0] & 0xffffu, w[1] & 0xffffu, w[2] & 0xffffu, w[3] & 0xffffu);
-            *reinterpret_cast<uint4 *>(dst + TABLE_B) = make_uint4(w[0] << 16, w[1] << 16, w[2] << 16, w[3] << 16);
-        } else {
-            *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        mbar_wait(mbar, 0);
     }
-    __syncthreads();
 
     const uint32_t prof_lane = (uint32_t)__cvta_generic_to_shared(s_prof) +
                                (prof_copies(G) > 1 ? (grp & 1) * (COPY_B + 64) : 0) + t * P * 16;
@@ -400,6 +452,7 @@ int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
             return OSW_E_CUDA;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
+    profile_build_kernel<G, R, PD><<<32, 256, 0, st>>>(a);
     sw_u16_kernel<G, R, THREADS, PD><<<n_sms, THREADS, smem, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? OSW_OK : OSW_E_CUDA;
 }
