@@ -249,14 +249,16 @@ extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *
     if (!c || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return OSW_E_ARG;
     if (n_seqs && (!residues || !offsets)) return OSW_E_ARG;
     if (n_seqs > 0xffffffffull) return OSW_E_ARG;
-    // Work-unit size: 4096 residues for large databases (1.5 % pipeline fill per chunk); smaller
-    // for small ones so that every group of lanes on every SM gets several chunks.
+    // Work-unit size: 8192 residues for large databases (0.8 % pipeline fill per chunk; measured
+    // best together with the quarter-size chunks at the end of the queue); smaller for small
+    // databases so that every group of lanes on every SM gets several chunks.
     uint32_t chunk_cols = OSW_CHUNK_COLS_DEFAULT;
     if (n_seqs) {
         const uint64_t per_dev = offsets[n_seqs] / ((uint64_t)shard_count * (uint64_t)c->n_dev);
-        const uint64_t fit = per_dev / 40000;            // ~ 148 SMs x 16 warps x 8 groups x 2
+        const uint64_t fit = per_dev / 25000;            // ~ 148 SMs x 12 warps x 8 groups x 2
         if (fit < chunk_cols) chunk_cols = (uint32_t)(fit < 256 ? 256 : fit);
     }
+    if (const char *e = getenv("OSW_CHUNK_COLS")) { const int v = atoi(e); if (v >= 64) chunk_cols = (uint32_t)v; }   // experiments
     if (max_chunk_residues && max_chunk_residues < chunk_cols) chunk_cols = (uint32_t)max_chunk_residues;
     const uint32_t n_shards = (uint32_t)shard_count * (uint32_t)c->n_dev;
     c->db_loaded = false;

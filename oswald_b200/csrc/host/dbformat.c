@@ -15,8 +15,15 @@
 typedef void (*chunk_cb)(void *user, uint64_t chunk_index, uint64_t first_seq, uint64_t n_seqs, uint64_t n_cols);
 static uint64_t walk_chunks(const uint64_t *off, uint64_t n, uint32_t chunk_cols, chunk_cb cb, void *user) {
     uint64_t c = 0, first = 0, cols = 0;
+    /* The walk goes from the shortest sequences to the longest; the GPU takes chunks in the opposite
+     * order.  The chunks taken LAST (the first twelfth of the residues here) are a quarter of the
+     * size: fine-grained work to even out the end of a launch, coarse work (less pipeline fill)
+     * before it. */
+    const uint64_t fine_until = n ? off[n] / 12 : 0;
+    const uint32_t coarse = chunk_cols, fine = chunk_cols >= 1024 ? chunk_cols / 4 : chunk_cols;
     for (uint64_t i = 0; i < n; ++i) {
         uint64_t len = off[i + 1] - off[i];
+        chunk_cols = off[i] < fine_until ? fine : coarse;
         /* empty sequences (they lead the ascending order) have no column, so they cannot share a
          * chunk with real ones: the kernel counts sequences by their LAST columns */
         if (i > first && (cols + len > chunk_cols || (cols == 0 && len > 0))) {

@@ -5,7 +5,8 @@
  *
  * The canonical database (stable ascending length order, sequences.c:1130-1225) is cut into
  * CHUNKS of consecutive whole sequences holding about `chunk_cols` residues each (one longer
- * sequence is a chunk of its own).  Because the order is by length, a chunk is a length bin:
+ * sequence is a chunk of its own; the chunks of the shortest sequences, which the GPU takes last,
+ * are a quarter of that size to even out the end of a launch).  Because the order is by length, a chunk is a length bin:
  * all its sequences have (nearly) the same length.  A chunk is stored as a COLUMN STREAM, one
  * byte per residue:
  *      bits 0-4  residue code 0..23
@@ -39,7 +40,7 @@ extern "C" {
 #define OSW_COL_LAST  0x40
 #define OSW_COL_PADBYTE 23           /* pad residue, no flags */
 #define OSW_CHUNK_ALIGN 128
-#define OSW_CHUNK_COLS_DEFAULT 4096
+#define OSW_CHUNK_COLS_DEFAULT 8192
 
 typedef struct osw_chunk {
     uint64_t stream_off;   /* byte offset of the first column in the shard stream */
