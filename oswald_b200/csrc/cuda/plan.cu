@@ -55,8 +55,8 @@ int lanes_needed(const Track &tr, const uint32_t *q_len, size_t cur, uint32_t do
 
 }  // namespace
 
-// Pair-database mode reads 8-row profile vectors: rows per lane are a multiple of 8.
-static bool pd_ok(int R) { return R % 8 == 0; }
+// Pair-database mode keeps two score tables in shared memory: with 32 lanes at most 28 rows each.
+static int pd_rmax(int G) { return G == 32 ? 28 : 40; }
 
 extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes, int mode, int min_g) {
     if (!q_len || nq < 1 || !out || max_passes < 1) return -1;
@@ -90,13 +90,13 @@ extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int 
     int n = 0;
     // Several passes: as few as the tallest geometry allows, then the smallest R that still fits
     // that many passes (1000 rows are two passes of 32 x 16, not 32 x 28 + 32 x 16).
-    const int r_cap = kRmax;                       // (a multiple of 8: fine for both modes)
+    const int r_cap = pair_db ? std::min(kRmax, pd_rmax(32)) : kRmax;
     int r_full = r_cap;
     {
         const int need_cap = std::max(lanes_needed(tr[0], q_len, 0, 0, r_cap), lanes_needed(tr[1], q_len, 0, 0, r_cap));
         const int n_min = (need_cap + 31) / 32;
         for (int ri = 7; ri >= 0; --ri) {
-            if (kR[ri] > r_cap || (pair_db && !pd_ok(kR[ri]))) continue;
+            if (kR[ri] > r_cap) continue;
             const int need = std::max(lanes_needed(tr[0], q_len, 0, 0, kR[ri]), lanes_needed(tr[1], q_len, 0, 0, kR[ri]));
             if ((need + 31) / 32 <= n_min) r_full = kR[ri];
         }
@@ -109,7 +109,7 @@ extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int 
         uint64_t best = ~0ull;
         for (int gi = 0; gi < 4; ++gi)
             for (int ri = 0; ri < 8; ++ri) {
-                if (kR[ri] > kRmax || (pair_db && !pd_ok(kR[ri]))) continue;
+                if (kR[ri] > kRmax || (pair_db && kR[ri] > pd_rmax(kG[gi]))) continue;
                 const int need = std::max(lanes_needed(tr[0], q_len, cur[0], done[0], kR[ri]),
                                           lanes_needed(tr[1], q_len, cur[1], done[1], kR[ri]));
                 if (need > kG[gi] || kG[gi] < min_g) continue;

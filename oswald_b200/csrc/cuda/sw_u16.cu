@@ -9,7 +9,6 @@ int osw_launch_u16(const U16Params &p, const OswPass &pass, int n_sms, cudaStrea
     a.has_in = pass.has_in && p.bound ? 1u : 0u;
     a.has_out = pass.has_out && p.bound ? 1u : 0u;
     a.pair_db = pass.pair_db ? 1u : 0u;
-    a.k65536 = 65536u;
     if ((pass.has_in || pass.has_out) && !p.bound) return OSW_E_ARG;
     const uint32_t goe = (uint32_t)p.gap_open_extend, ge = (uint32_t)p.gap_extend;
     const uint32_t B = goe + ge + 32u;

@@ -57,13 +57,10 @@ namespace osw_u16 {
 constexpr uint32_t FLAG_THRESHOLD = 65504;      // biased maximum at/above which a pair is re-scored
 constexpr int RING = 64;                        // ring entries per group (two halves of 32)
 
-// A profile "vector" is one 16-byte table entry: the scores of RV consecutive rows for one residue
-// (RV = 4 packed row pairs in two-track mode, 8 single 16-bit scores in pair-database mode).
-__host__ __device__ constexpr int rows_per_vec(bool PD) { return PD ? 8 : 4; }
-__host__ __device__ constexpr int pitch_vecs(int R, int RV) { return (R / RV) | 1; }          // odd, >= R/RV
-__host__ __device__ constexpr int prof_vecs(int G, int R, int RV) { return (G * pitch_vecs(R, RV) + 7) / 8 * 8; }
+__host__ __device__ constexpr int pitch_quads(int R) { return (R / 4) | 1; }          // odd, >= R/4
+__host__ __device__ constexpr int prof_quads(int G, int R) { return (G * pitch_quads(R) + 7) / 8 * 8; }
 __host__ __device__ constexpr int prof_copies(int G) { return G == 4 ? 2 : 1; }
-__host__ __device__ constexpr size_t prof_copy_bytes(int G, int R, int RV) { return (size_t)24 * prof_vecs(G, R, RV) * 16; }
+__host__ __device__ constexpr size_t prof_copy_bytes(int G, int R) { return (size_t)24 * prof_quads(G, R) * 16; }
 __host__ __device__ constexpr int block_threads(int R) { return R > 32 ? 384 : 512; }
 // (OSW_EXP_* macros: timing experiments only - each one breaks the results; never set in the product build.)
 // A lane's R rows are swept as NUM_CHAINS independent segments (segment c works one column
@@ -72,7 +69,7 @@ __host__ __device__ constexpr int block_threads(int R) { return R > 32 ? 384 : 5
 #define OSW_NUM_CHAINS 2
 #endif
 constexpr int NUM_CHAINS = OSW_NUM_CHAINS;
-__host__ __device__ constexpr int seg_begin(int NV, int NC, int c) { return (NV * c + NC - 1) / NC; }   // first vector of segment c (NV vectors per lane)
+__host__ __device__ constexpr int seg_begin(int R, int NC, int c) { return ((R / 4) * c + NC - 1) / NC; }   // first quad of segment c
 
 // mailbox / ring traffic: ordered against __syncwarp
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -92,16 +89,7 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     return v;
 }
 // profile reads: the profile is constant once built, so the compiler may schedule these freely
-// (n >> 16) | (h << 16) without the shift/permute instructions (they share the DPX pipe): a
-// multiply-high and a multiply-add on the FMA pipe; k = 65536 comes from the kernel arguments so
-// that the compiler keeps the multiplies.  Measured no faster than one PRMT (the default); kept
-// behind OSW_PD_FMA_PACK.
-__device__ __forceinline__ uint32_t pack_high_rows(uint32_t n, uint32_t h, uint32_t k) {
-    uint32_t hi, r;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(n), "r"(k));
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(h), "r"(k), "r"(hi));
-    return r;
-}
+__device__ __forceinline__ uint4 add4(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ uint4 lds128_const(uint32_t addr) {
     uint4 v;
     asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -113,61 +101,44 @@ struct KArgs {
     OswLaneDesc lane[2][32]; // [half][lane of group]: which query rows the lane holds
     uint32_t has_in, has_out;
     uint32_t pair_db;        // PD mode (host-side dispatch only)
-    uint32_t k65536;         // 65536, opaque to the compiler (see pack_high_rows)
     uint32_t bias2;          // B | B<<16
     uint32_t nge2;           // (-ge) & 0xffff, both halves
     uint32_t ngoe_word;      // -(goe | goe<<16) as a 32-bit two's complement
     uint32_t bias;           // B
 };
 
-// One 16-byte profile vector (RV rows x one residue) written at its place in a table image starting
-// at `base` (shared or global memory).  Two-track mode: word r = (track-0 score, track-1 score) of
-// row r.  Pair-database mode (both halves work on track 0): two tables of 16-bit scores, N with the
-// row pairs in natural order (row 2k low, row 2k+1 high) and S with them swapped, so that the score
-// words of two rows against residues (a, b) are  (N[a] & 0xffff) | (S[b] & 0xffff0000)  and
-// (N[a] >> 16) | (S[b] << 16).
+// One 16-byte profile entry (4 rows x one residue) - and its high-half twin in pair-database mode -
+// written at its place in a table image starting at `base` (shared or global memory).
 template <int G, int R, bool PD>
 __device__ __forceinline__ void profile_entry(int idx, const KArgs &a, const int *s_mat, unsigned char *base) {
-    constexpr int RV = rows_per_vec(PD);
-    constexpr int P = pitch_vecs(R, RV);
-    constexpr int VECS = prof_vecs(G, R, RV);
-    constexpr int PITCH_B = VECS * 16;
-    constexpr int COPY_B = (int)prof_copy_bytes(G, R, RV);
+    constexpr int P = pitch_quads(R);
+    constexpr int PITCH_B = prof_quads(G, R) * 16;
+    constexpr int COPY_B = (int)prof_copy_bytes(G, R);
     constexpr int TABLE_B = COPY_B * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0);
     const U16Params &p = a.p;
-    const int copy = idx / (24 * VECS);
-    const int rem = idx % (24 * VECS);
-    const int b = rem / VECS, slot = rem % VECS;
+    const int copy = idx / (24 * prof_quads(G, R));
+    const int rem = idx % (24 * prof_quads(G, R));
+    const int b = rem / prof_quads(G, R), slot = rem % prof_quads(G, R);
     const int tt = slot / P, k = slot % P;
-    int sa[RV], sb[RV];
-#pragma unroll
-    for (int r = 0; r < RV; ++r) { sa[r] = 0; sb[r] = 0; }
-    if (tt < G && k < R / RV) {
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (tt < G && k < R / 4) {
         const OswLaneDesc da = a.lane[0][tt], db = a.lane[1][tt];
         const uint8_t *qa = da.q_len ? p.queries + p.q_off[da.query] : p.queries;
         const uint8_t *qb = db.q_len ? p.queries + p.q_off[db.query] : p.queries;
-#pragma unroll
-        for (int r = 0; r < RV; ++r) {
-            const uint32_t ra = da.row0 + RV * k + r, rb = db.row0 + RV * k + r;
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t ra = da.row0 + 4 * k + r, rb = db.row0 + 4 * k + r;
             const int ca = ra < da.q_len ? qa[ra] : OSW_PAD_CODE;
             const int cb = rb < db.q_len ? qb[rb] : OSW_PAD_CODE;
-            sa[r] = s_mat[ca * 32 + b]; sb[r] = s_mat[cb * 32 + b];
+            if (PD) w[r] = (uint32_t)s_mat[ca * 32 + b];            // track 0 only; split into halves below
+            else w[r] = ((uint32_t)s_mat[ca * 32 + b] & 0xffffu) | ((uint32_t)s_mat[cb * 32 + b] << 16);
         }
     }
     // the second copy (G == 4) sits 64 bytes further modulo 128, i.e. 4 bank groups away
     unsigned char *dst = base + copy * (COPY_B + 64) + b * PITCH_B + slot * 16;
-    uint32_t w[4], v[4];
     if (PD) {
-#pragma unroll
-        for (int k2 = 0; k2 < 4; ++k2) {
-            w[k2] = ((uint32_t)sa[2 * k2] & 0xffffu) | ((uint32_t)sa[2 * k2 + 1] << 16);       // N: natural
-            v[k2] = ((uint32_t)sa[2 * k2 + 1] & 0xffffu) | ((uint32_t)sa[2 * k2] << 16);       // S: swapped
-        }
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4 *>(dst + TABLE_B) = make_uint4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0] & 0xffffu, w[1] & 0xffffu, w[2] & 0xffffu, w[3] & 0xffffu);
+        *reinterpret_cast<uint4 *>(dst + TABLE_B) = make_uint4(w[0] << 16, w[1] << 16, w[2] << 16, w[3] << 16);
     } else {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) w[r] = ((uint32_t)sa[r] & 0xffffu) | ((uint32_t)sb[r] << 16);
         *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
@@ -179,7 +150,7 @@ __global__ void __launch_bounds__(256) profile_build_kernel(const KArgs a) {
     __shared__ int s_mat[24 * 32];
     for (int i = threadIdx.x; i < 24 * 32; i += 256) s_mat[i] = a.p.matrix[i];
     __syncthreads();
-    const int n = prof_copies(G) * 24 * prof_vecs(G, R, rows_per_vec(PD));
+    const int n = prof_copies(G) * 24 * prof_quads(G, R);
     for (int idx = blockIdx.x * 256 + threadIdx.x; idx < n; idx += gridDim.x * 256)
         profile_entry<G, R, PD>(idx, a, s_mat, a.p.profile);
 }
@@ -212,12 +183,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 sw_u16_kernel(const KArgs a) {
     constexpr int WARPS = THREADS / 32;
     constexpr int GROUPS = 32 / G;              // groups per warp
-    constexpr int RV = rows_per_vec(PD);       // rows per profile vector
-    constexpr int NV = R / RV;                  // vectors per lane
-    static_assert(R % RV == 0, "rows per lane must be a multiple of the profile vector height");
-    constexpr int P = pitch_vecs(R, RV);
-    constexpr int PITCH_B = prof_vecs(G, R, RV) * 16;
-    constexpr int COPY_B = (int)prof_copy_bytes(G, R, RV);
+    constexpr int P = pitch_quads(R);
+    constexpr int PITCH_B = prof_quads(G, R) * 16;
+    constexpr int COPY_B = (int)prof_copy_bytes(G, R);
     constexpr int EPL = 32 / G;                 // ring entries each lane fills per 32-column block
     constexpr int NC = NUM_CHAINS;              // independent row segments per lane
 
@@ -225,7 +193,7 @@ sw_u16_kernel(const KArgs a) {
     // layout: [profile copies][mailbox: WARPS*32 uint4][rings: WARPS*GROUPS*RING uint4][out rings: WARPS*32 uint2]
     unsigned char *s_prof = smem;
     constexpr int TABLE_B = COPY_B * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0);
-    constexpr int PROF_B = TABLE_B * (PD ? 2 : 1);           // PD: natural-order table, then swapped table
+    constexpr int PROF_B = TABLE_B * (PD ? 2 : 1);           // PD: low-half table, then high-half table
     uint4 *s_mail = reinterpret_cast<uint4 *>(smem + PROF_B);
     uint4 *s_ring = s_mail + WARPS * 32;
     uint2 *s_oring = reinterpret_cast<uint2 *>(s_ring + WARPS * GROUPS * RING);     // [WARPS][32] bottom rows of the last 32 steps
@@ -365,7 +333,7 @@ sw_u16_kernel(const KArgs a) {
                     for (int c = 0; c < NC; ++c) {
                         if (msg[c].w & OSW_COL_FIRST) {
 #pragma unroll
-                            for (int r = RV * seg_begin(NV, NC, c); r < RV * seg_begin(NV, NC, c + 1); ++r) { Hl[r] = B2; E[r] = B2; }
+                            for (int r = 4 * seg_begin(R, NC, c); r < 4 * seg_begin(R, NC, c + 1); ++r) { Hl[r] = B2; E[r] = B2; }
                             diag[c] = B2;
                         }
                     }
@@ -373,57 +341,41 @@ sw_u16_kernel(const KArgs a) {
 #endif
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    paddr[c] = prof_lane + (msg[c].w & OSW_COL_CODE) * PITCH_B + seg_begin(NV, NC, c) * 16;
-                    paddr_hi[c] = PD ? prof_lane + TABLE_B + ((msg[c].w >> 8) & OSW_COL_CODE) * PITCH_B + seg_begin(NV, NC, c) * 16 : 0u;
+                    paddr[c] = prof_lane + (msg[c].w & OSW_COL_CODE) * PITCH_B + seg_begin(R, NC, c) * 16;
+                    paddr_hi[c] = PD ? prof_lane + TABLE_B + ((msg[c].w >> 8) & OSW_COL_CODE) * PITCH_B + seg_begin(R, NC, c) * 16 : 0u;
                 }
-                // score words of the RV rows of profile vector kk of segment c
-                auto load_scores = [&](int c, int kk, uint32_t (&sc)[RV]) {
-                    const uint4 n = lds128_const(paddr[c] + kk * 16);
-                    if (PD) {
-                        const uint4 h = lds128_const(paddr_hi[c] + kk * 16);
-                        const uint32_t nn[4] = {n.x, n.y, n.z, n.w}, hh[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-                        for (int k2 = 0; k2 < 4; ++k2) {
-                            sc[(2 * k2) % RV] = (nn[k2] & 0x0000ffffu) | (hh[k2] & 0xffff0000u);             // one LOP3
-#ifdef OSW_PD_FMA_PACK
-                            sc[(2 * k2 + 1) % RV] = pack_high_rows(nn[k2], hh[k2], a.k65536);                // two FMA-pipe ops
-#else
-                            sc[(2 * k2 + 1) % RV] = __byte_perm(nn[k2], hh[k2], 0x5432);                     // (n >> 16) | (h << 16)
-#endif
-                        }
-                    } else {
-                        sc[0] = n.x; sc[1] = n.y; sc[2] = n.z; sc[3] = n.w;
-                    }
-                };
                 // Row sweeps of the NC segments, interleaved: they are independent dependency
                 // chains.  t (the diagonal term) of row r+1 is issued before H of row r is written,
                 // so that H can overwrite Hl[r] in place.
                 uint32_t F[NC], cm[NC], Heven[NC], t_next[NC];
-                uint32_t sv[NC][RV];
+                uint4 sv[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     F[c] = msg[c].y; cm[c] = msg[c].z; Heven[c] = B2;
-                    load_scores(c, 0, sv[c]);
-                    t_next[c] = __viaddmax_u16x2(diag[c], sv[c][0], E[RV * seg_begin(NV, NC, c)]);
+                    sv[c] = lds128_const(paddr[c]);
+                    if (PD) sv[c] = add4(sv[c], lds128_const(paddr_hi[c]));
+                    t_next[c] = __viaddmax_u16x2(diag[c], sv[c].x, E[4 * seg_begin(R, NC, c)]);
                 }
 #pragma unroll
-                for (int kk = 0; kk < seg_begin(NV, NC, 1); ++kk) {
-                    uint32_t sn[NC][RV];
+                for (int kk = 0; kk < seg_begin(R, NC, 1); ++kk) {
+                    uint4 sn[NC];
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
-#pragma unroll
-                        for (int r = 0; r < RV; ++r) sn[c][r] = sv[c][r];
-                        if (kk + 1 < seg_begin(NV, NC, c + 1) - seg_begin(NV, NC, c)) load_scores(c, kk + 1, sn[c]);
+                        sn[c] = sv[c];
+                        if (kk + 1 < seg_begin(R, NC, c + 1) - seg_begin(R, NC, c)) {
+                            sn[c] = lds128_const(paddr[c] + (kk + 1) * 16);
+                            if (PD) sn[c] = add4(sn[c], lds128_const(paddr_hi[c] + (kk + 1) * 16));
+                        }
                     }
 #pragma unroll
-                    for (int rr = 0; rr < RV; ++rr) {
+                    for (int rr = 0; rr < 4; ++rr) {
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
-                            if (kk < seg_begin(NV, NC, c + 1) - seg_begin(NV, NC, c)) {
-                                const int r = RV * (seg_begin(NV, NC, c) + kk) + rr;
-                                const uint32_t s_after = rr + 1 < RV ? sv[c][(rr + 1) % RV] : sn[c][0];
+                            if (kk < seg_begin(R, NC, c + 1) - seg_begin(R, NC, c)) {
+                                const int r = 4 * (seg_begin(R, NC, c) + kk) + rr;
+                                const uint32_t s_after = rr == 0 ? sv[c].y : rr == 1 ? sv[c].z : rr == 2 ? sv[c].w : sn[c].x;
                                 const uint32_t tt = t_next[c];
-                                if (r + 1 < RV * seg_begin(NV, NC, c + 1)) t_next[c] = __viaddmax_u16x2(Hl[r], s_after, E[r + 1]);
+                                if (r + 1 < 4 * seg_begin(R, NC, c + 1)) t_next[c] = __viaddmax_u16x2(Hl[r], s_after, E[r + 1]);
                                 const uint32_t H = __vimax3_u16x2(tt, F[c], B2);
                                 const uint32_t u = H - GOE2;
                                 E[r] = __viaddmax_u16x2(E[r], NGE, u);
@@ -438,16 +390,14 @@ sw_u16_kernel(const KArgs a) {
                         }
                     }
 #pragma unroll
-                    for (int c = 0; c < NC; ++c)
-#pragma unroll
-                        for (int r = 0; r < RV; ++r) sv[c][r] = sn[c][r];
+                    for (int c = 0; c < NC; ++c) sv[c] = sn[c];
                 }
                 // hand the segments' bottom rows on: segment c -> segment c+1 (next step), last -> next lane
 #pragma unroll
                 for (int c = 0; c < NC; ++c) diag[c] = msg[c].x;
 #pragma unroll
                 for (int c = NC - 1; c >= 1; --c)
-                    mid[c] = make_uint4(Hl[RV * seg_begin(NV, NC, c) - 1], F[c - 1], cm[c - 1], msg[c - 1].w);
+                    mid[c] = make_uint4(Hl[4 * seg_begin(R, NC, c) - 1], F[c - 1], cm[c - 1], msg[c - 1].w);
                 const uint32_t lf = msg[NC - 1].w;
                 const uint32_t Hbot = Hl[R - 1], Fbot = F[NC - 1], cmbot = cm[NC - 1];
                 run = __vmaxu2(run, cmbot);
@@ -491,7 +441,7 @@ sw_u16_kernel(const KArgs a) {
 
 template <int G, int R, int THREADS, bool PD>
 int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
-    const size_t prof = (prof_copy_bytes(G, R, rows_per_vec(PD)) * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0)) * (PD ? 2 : 1);
+    const size_t prof = (prof_copy_bytes(G, R) * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0)) * (PD ? 2 : 1);
     const size_t smem = prof + (size_t)(THREADS / 32) * 32 * 16 + (size_t)(THREADS / 32) * (32 / G) * RING * 16 + (size_t)(THREADS / 32) * 32 * 8;
     static bool configured[64] = {};          // the attribute is per device
     int dev = 0;
@@ -511,10 +461,7 @@ int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
 template <int G, int R>
 int launch_one(const KArgs &a, int n_sms, cudaStream_t st) {
     constexpr int THREADS = block_threads(R);
-    if (a.pair_db) {
-        if constexpr (R % 8 == 0) return launch_threads<G, R, THREADS, true>(a, n_sms, st);
-        else return OSW_E_ARG;                  // pair-database plans use 8-row vectors (plan.cu)
-    }
+    if (a.pair_db) return launch_threads<G, R, THREADS, true>(a, n_sms, st);
     return launch_threads<G, R, THREADS, false>(a, n_sms, st);
 }
 

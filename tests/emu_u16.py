@@ -31,9 +31,7 @@ def build_stream(seqs):
 
 
 def segment_rows(R, chains):
-    """Row counts of the segments a lane's R rows are split into (like seg_begin() in the kernel,
-    in units of 4 rows; the kernel uses 8-row units in pair-database mode - the split point does not
-    change any result)."""
+    """Row counts of the segments a lane's R rows are split into (seg_begin() in sw_u16.cu)."""
     q = R // 4
     begin = [(q * c + chains - 1) // chains for c in range(chains + 1)]
     return [4 * (begin[c + 1] - begin[c]) for c in range(chains)]
