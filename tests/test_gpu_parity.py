@@ -298,3 +298,24 @@ def test_fuzz_small_cases(searcher):
         searcher.load_db(db, max_chunk_residues=int(rng.choice([0, 0, 32, 200, 1000])))
         mode = list(MODES.values())[case % 3]
         check(searcher, db, q, name, go, ge, top, mask=mode)
+
+
+def test_cli_two_gpus_same_report(built, tmp_path):
+    """`-f 2` (two GPUs in one process) prints the same hit blocks as `-f 1`."""
+    import ctypes as C, gzip, os, shutil, subprocess
+    n = C.c_int(0)
+    built.osw_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    cli = os.path.join(os.path.dirname(capi.LIB_PATH), "oswald")
+    meta = load_case("g2_overflow")
+    for src, dst in ((meta["db_fasta"], "db.fasta"), (meta["q_fasta"], "q.fasta")):
+        with gzip.open(src, "rb") as g, open(tmp_path / dst, "wb") as f:
+            shutil.copyfileobj(g, f)
+    subprocess.run([cli, "-O", "preprocess", "-i", "db.fasta", "-o", "db"], cwd=tmp_path, check=True)
+    outs = []
+    for f in ("1", "2"):
+        out = subprocess.run([cli, "-O", "search", "-q", "q.fasta", "-d", "db", "-s", "pam30", "-g", "9", "-e", "1", "-r", "12", "-f", f],
+                             cwd=tmp_path, check=True, capture_output=True, text=True).stdout
+        outs.append(out.split("\nSearch date:")[0].split("Query filename:")[1])
+    assert outs[0] == outs[1]
