@@ -18,6 +18,8 @@
 //     residues are.  In pair-database mode (template flag PD; single or lopsided query sets) both
 //     halves work on the same query rows against two database sequences zipped in the pair
 //     stream, and a row's score word is the sum of a low-half and a high-half table entry.
+//     The table image is built once per pass in global memory (profile_build_kernel) and every CTA
+//     brings it into shared memory with TMA bulk copies completing on an mbarrier.
 //   * G lanes (4, 8, 16 or 32) form a systolic array over the query rows: lane t owns rows
 //     t*R .. t*R+R-1 (H of the previous column and E in registers), swept as two independent
 //     segments one column apart (two dependency chains per thread keep the DPX pipe fed).  A
