@@ -460,10 +460,13 @@ int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
 }
 
 // CTA size: 512 threads (128 registers each) up to R = 32, 384 (168 registers) above.
+#ifndef OSW_PD_THREADS
+#define OSW_PD_THREADS 0        // experiment: CTA size of the pair-database kernels (0 = same rule as two-track)
+#endif
 template <int G, int R>
 int launch_one(const KArgs &a, int n_sms, cudaStream_t st) {
     constexpr int THREADS = block_threads(R);
-    if (a.pair_db) return launch_threads<G, R, THREADS, true>(a, n_sms, st);
+    if (a.pair_db) return launch_threads<G, R, (OSW_PD_THREADS ? OSW_PD_THREADS : THREADS), true>(a, n_sms, st);
     return launch_threads<G, R, THREADS, false>(a, n_sms, st);
 }
 
