@@ -292,3 +292,34 @@ def test_planned_passes_model_matches_oracle(built, lens, monkeypatch):
     got = emu_u16.score_with_plan(passes, seqs, queries, mat, 10, 2)
     want = np.array([[O.sw_score(q, s, mat, 10, 2) for s in seqs] for q in queries])
     assert np.array_equal(got, want)
+
+
+def test_cli_fasta_edge_cases(built, tmp_path):
+    """The single-pass FASTA reader: CRLF line ends, a last line without newline, blank lines, lower
+    case and other non-letters (-> dummy residue 23), an empty record, multi-line sequences."""
+    import subprocess
+    cli = _cli()
+    text = (">first record\r\nACDEFG\r\nHIKLMN\r\n"
+            ">empty\n"
+            ">weird letters\nAC*-acx\n\nJOUZ\n"
+            ">last one, no newline\nWWWW")
+    (tmp_path / "in.fasta").write_bytes(text.encode())
+    subprocess.run([cli, "-O", "preprocess", "-i", "in.fasta", "-o", "db"], cwd=tmp_path, check=True)
+    n, d, mt = open(tmp_path / "db.info").read().split()
+    assert (int(n), int(d)) == (4, 0 + 4 + 11 + 12)
+    raw = open(tmp_path / "db.seq", "rb").read()
+    lens = list(np.frombuffer(raw[:8], dtype="<u2"))
+    assert lens == [0, 4, 11, 12]                                   # stable ascending length
+    res = np.frombuffer(raw[8:], dtype=np.uint8)
+    assert list(res[:4]) == [19, 19, 19, 19]                        # WWWW
+    assert list(res[4:15]) == [0, 2, 23, 23, 23, 23, 23, 23, 23, 23, 22]      # A C * - a c x J O U Z
+    assert list(res[15:]) == list(ob.encode("ACDEFGHIKLMN"))
+    assert [l.rstrip("\n") for l in open(tmp_path / "db.desc")] == [">empty", ">last one, no newline", ">weird letters", ">first record"]
+    assert int(mt) == len(">last one, no newline") + 2
+
+
+def test_cli_rejects_too_long_sequences(built, tmp_path):
+    import subprocess
+    (tmp_path / "in.fasta").write_text(">long\n" + "A" * 65536 + "\n")
+    r = subprocess.run([_cli(), "-O", "preprocess", "-i", "in.fasta", "-o", "db"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0 and "65535" in r.stdout
