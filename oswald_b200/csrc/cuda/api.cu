@@ -47,7 +47,7 @@ struct DevState {
     uint32_t *d_qoff = nullptr; size_t qoff_cap = 0;
     int8_t *d_matrix = nullptr;
     int2 *d_scratch = nullptr; size_t scratch_cap = 0;
-    uint2 *d_bound = nullptr;                  // bottom rows handed from pass to pass (in place)
+    uint2 *d_bound = nullptr; size_t bound_cap = 0;   // bottom rows handed from pass to pass (in place), one segment of chunks at a time
     unsigned char *d_profile[2] = {nullptr, nullptr};   // profile table images, one per stream
     uint2 *d_pairs = nullptr; uint32_t pairs_cap = 0;
     uint32_t *d_counters = nullptr;            // [0] flagged count, [1..] chunk counters per launch
@@ -87,7 +87,7 @@ void free_db(DevState &d) {
     if (d.h_pair) cudaFreeHost(d.h_pair);
     d.h_pair = nullptr;
     cudaFree(d.d_stream); cudaFree(d.d_chunks); cudaFree(d.d_canon); cudaFree(d.d_seq_off); cudaFree(d.d_seq_len);
-    cudaFree(d.d_bound);
+    cudaFree(d.d_bound); d.bound_cap = 0;
     d.d_stream = nullptr; d.d_chunks = nullptr; d.d_canon = nullptr; d.d_seq_off = nullptr; d.d_seq_len = nullptr;
     d.d_bound = nullptr;
     if (d.h_stream) cudaFreeHost(d.h_stream);
@@ -393,10 +393,17 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
         flag_cap = d.pairs_cap;
         bool need_bound = false;
         for (const OswPass &p : passes) need_bound |= p.has_in || p.has_out;
-        if (need_bound && !d.d_bound) {
-            const size_t cols = std::max<uint64_t>(std::max<uint64_t>(s.stream_bytes, s.pair_cols), 1);
-            CK(cudaMalloc(&d.d_bound, cols * sizeof(uint2)));
-            CK(cudaMemsetAsync(d.d_bound, 0, cols * sizeof(uint2), d.st));
+        if (need_bound) {
+            // The bottom rows take 8 bytes per column - 8 x the database itself.  They are kept for one
+            // SEGMENT of consecutive chunks at a time (all passes run over a segment before the next
+            // one starts), so the buffer is bounded whatever the database size.
+            size_t budget_cols = (size_t)2 << 30;            // 16 GiB
+            if (const char *e = getenv("OSW_BOUND_BUDGET_COLS")) { const long long v = atoll(e); if (v >= 1024) budget_cols = (size_t)v; }
+            const size_t all_cols = std::max<uint64_t>(std::max<uint64_t>(s.stream_bytes, s.pair_cols), 1);
+            const size_t want = std::min(all_cols, budget_cols + 2 * 65536 + 1024);
+            const size_t had = d.bound_cap;
+            if ((rc = grow(&d.d_bound, &d.bound_cap, want)) != OSW_OK) return rc;
+            if (d.bound_cap != had) CK(cudaMemsetAsync(d.d_bound, 0, d.bound_cap * sizeof(uint2), d.st));   // (padding columns are read)
         }
     }
 
@@ -420,6 +427,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
         CK(cudaMemcpyAsync(d.d_pair, d.h_pair, 2 * s.pair_cols, cudaMemcpyHostToDevice, d.st));
     }
     if (use_u16 && N) {
+        uint64_t bound_col0 = 0;
         auto launch = [&](const OswPass &ps, uint32_t first, uint32_t end, cudaStream_t st) -> int {
             if (slot >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
             U16Params up;
@@ -428,7 +436,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             up.queries = d.d_queries; up.q_off = d.d_qoff; up.matrix = d.d_matrix;
             up.profile = d.d_profile[st == d.st2 ? 1 : 0];
             up.scores = d.d_scores; up.n_seqs = N;
-            up.bound = d.d_bound;
+            up.bound = d.d_bound; up.bound_col0 = bound_col0;
             up.gap_open_extend = go + ge; up.gap_extend = ge;
             up.chunk_counter = d.d_counters + 1 + slot;
             up.cycle_acc = d.d_cycles + slot;
@@ -464,9 +472,32 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             CK(cudaStreamWaitEvent(d.st, d.ev_join, 0));
         } else {
             // One launch per pass, in order: a pass reads the bottom row the previous one parked (in
-            // place: a warp writes a chunk's columns behind the ones it still has to read).
-            for (const OswPass &ps : passes)
-                if ((rc = launch(ps, 0, s.n_chunks, d.st)) != OSW_OK) return rc;
+            // place: a warp writes a chunk's columns behind the ones it still has to read).  With
+            // several passes the chunk list is cut into segments whose bottom rows fit the buffer;
+            // chunks are stored back to back in ascending order, so a range of the (descending)
+            // directory is one contiguous stretch of the stream.
+            const bool pd = !passes.empty() && passes[0].pair_db;
+            auto chunk_begin = [&](uint32_t k) { return pd ? s.chunks[k].pair_off : s.chunks[k].stream_off; };
+            auto chunk_end = [&](uint32_t k) {
+                const uint64_t n = pd ? s.chunks[k].n_pair_cols : s.chunks[k].n_cols, al = pd ? 64 : OSW_CHUNK_ALIGN;
+                return chunk_begin(k) + (n + al - 1) / al * al;
+            };
+            uint32_t seg_first = 0;
+            while (seg_first < s.n_chunks) {
+                uint32_t seg_end = s.n_chunks;
+                if (d.d_bound && passes.size() > 1) {
+                    seg_end = seg_first + 1;
+                    while (seg_end < s.n_chunks && chunk_end(seg_first) - chunk_begin(seg_end) <= d.bound_cap) ++seg_end;
+                    bound_col0 = chunk_begin(seg_end - 1);
+                    if (chunk_end(seg_first) - bound_col0 > d.bound_cap) {
+                        snprintf(g_err, sizeof g_err, "a chunk is larger than the bottom-row buffer");
+                        return OSW_E_NOMEM;
+                    }
+                }
+                for (const OswPass &ps : passes)
+                    if ((rc = launch(ps, seg_first, seg_end, d.st)) != OSW_OK) return rc;
+                seg_first = seg_end;
+            }
         }
         CK(cudaEventRecord(d.ev[1], d.st));
         *launches += osw_collect_flagged(d.d_scores, N, nq, d.d_pairs, d.d_counters, flag_cap, d.st);

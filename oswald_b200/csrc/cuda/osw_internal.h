@@ -69,7 +69,9 @@ struct U16Params {
     unsigned char   *profile;    // global image of the pass's profile table (>= OSW_PROFILE_BYTES), private to the stream
     int32_t         *scores;     // [nq][n_seqs]
     uint64_t         n_seqs;
-    uint2           *bound;      // [max(stream_bytes, pair_cols)] (H,F) bottom row handed from pass to pass, in place; or nullptr
+    uint2           *bound;      // (H,F) bottom rows handed from pass to pass, in place, for the columns
+                                 // [bound_col0, bound_col0 + capacity) of the (pair) stream; or nullptr
+    uint64_t         bound_col0;
     int              gap_open_extend, gap_extend;
     uint32_t        *chunk_counter;
     unsigned long long *cycle_acc;   // sum over CTAs of their elapsed clock64 cycles (one CTA per SM), or nullptr

@@ -319,3 +319,18 @@ def test_cli_two_gpus_same_report(built, tmp_path):
                              cwd=tmp_path, check=True, capture_output=True, text=True).stdout
         outs.append(out.split("\nSearch date:")[0].split("Query filename:")[1])
     assert outs[0] == outs[1]
+
+
+def test_segmented_bottom_rows(built, monkeypatch):
+    """Several passes with a bottom-row buffer that holds only a few chunks at a time."""
+    monkeypatch.setenv("OSW_BOUND_BUDGET_COLS", "2048")
+    rng = np.random.default_rng(88)
+    seqs = rand_seqs(rng, 1500, 1, 400) + [AA[rng.integers(0, 20, size=n)] for n in (3000, 70000)]
+    q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (1500, 2900, 1400)])
+    seqs[7] = q.query(2).copy()
+    db = make_db(seqs)
+    with ob.Searcher(1) as s:
+        s.load_db(db, max_chunk_residues=512)
+        for mode in MODES.values():
+            tm = check(s, db, q, "blosum62", 10, 2, 10, mask=mode)
+            assert tm["launches"] >= 30          # several segments x passes (unsegmented: 26 or fewer)
