@@ -511,6 +511,10 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
 
 }  // namespace
 
+static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_off, int nq,
+                        const int8_t *matrix, int go, int ge, int top_r,
+                        osw_hit *hits, uint32_t *n_hits, int32_t *all_scores, osw_timing *timing);
+
 extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_off, int nq,
                           const int8_t *matrix, int go, int ge, int top_r,
                           osw_hit *hits, uint32_t *n_hits, int32_t *all_scores, osw_timing *timing) {
@@ -525,6 +529,34 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
     // the 16-bit kernel's bias and wrap detection assume |score| <= 31 (the reference's tables span -17..17)
     for (int k = 0; k < 24 * 32; ++k)
         if (matrix[k] < -32 || matrix[k] > 31) { snprintf(g_err, sizeof g_err, "substitution score %d is outside -32..31", matrix[k]); return OSW_E_ARG; }
+    // The score matrix (4 bytes per query and sequence) is the largest per-search buffer: many
+    // queries go through in batches that keep it under 8 GiB per GPU (OSW_SCORE_BUDGET_KB overrides).
+    uint64_t n_max = 1;
+    for (int i = 0; i < c->n_dev; ++i) n_max = std::max<uint64_t>(n_max, c->devs[i].shard.n_seqs);
+    uint64_t budget = (uint64_t)8 << 30;
+    if (const char *e = getenv("OSW_SCORE_BUDGET_KB")) { const long long v = atoll(e); if (v >= 1) budget = (uint64_t)v << 10; }
+    const int batch = (int)std::max<uint64_t>(2, std::min<uint64_t>((uint64_t)nq, budget / (4 * n_max)));
+    osw_timing total;
+    memset(&total, 0, sizeof total);
+    for (int q0 = 0; q0 < nq; q0 += batch) {
+        const int nb = std::min(batch, nq - q0);
+        osw_timing tm;
+        int rc = search_batch(c, queries, q_off + q0, nb, matrix, go, ge, top_r, hits ? hits + (size_t)q0 * top_r : nullptr,
+                              n_hits ? n_hits + q0 : nullptr, all_scores ? all_scores + (size_t)q0 * c->n_seqs_canon : nullptr, &tm);
+        if (rc != OSW_OK) return rc;
+        total.device_ms += tm.device_ms; total.score_ms += tm.score_ms; total.rescore_ms += tm.rescore_ms; total.topr_ms += tm.topr_ms;
+        total.h2d_ms += tm.h2d_ms; total.wall_ms += tm.wall_ms; total.cells += tm.cells; total.padded_cells += tm.padded_cells;
+        total.rescored_pairs += tm.rescored_pairs; total.launches += tm.launches; total.sm_cycles += tm.sm_cycles;
+        total.db_stream_bytes += tm.db_stream_bytes;
+    }
+    if (timing) *timing = total;
+    return OSW_OK;
+}
+
+// One batch of queries: q_off points at the batch's first entry (offsets stay absolute).
+static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_off, int nq,
+                        const int8_t *matrix, int go, int ge, int top_r,
+                        osw_hit *hits, uint32_t *n_hits, int32_t *all_scores, osw_timing *timing) {
     const double t_wall0 = now_ms();
     std::vector<OswPass> passes, wide;
     if (c->kernel_mask & OSW_K_U16) {
@@ -663,7 +695,7 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
     }
     tm.h2d_ms = t_h2d - t_wall0;
     tm.wall_ms = now_ms() - t_wall0;
-    tm.cells = (uint64_t)q_off[nq] * c->residues_local;
+    tm.cells = (uint64_t)(q_off[nq] - q_off[0]) * c->residues_local;
     tm.padded_cells = padded;
     tm.rescored_pairs = rescored;
     tm.launches = launches;

@@ -334,3 +334,15 @@ def test_segmented_bottom_rows(built, monkeypatch):
         for mode in MODES.values():
             tm = check(s, db, q, "blosum62", 10, 2, 10, mask=mode)
             assert tm["launches"] >= 30          # several segments x passes (unsegmented: 26 or fewer)
+
+
+def test_query_batches(built, monkeypatch):
+    """Many queries are searched in batches that bound the score matrix; results are unchanged."""
+    monkeypatch.setenv("OSW_SCORE_BUDGET_KB", "8")
+    rng = np.random.default_rng(5)
+    db = make_db(rand_seqs(rng, 700, 1, 300))
+    q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (20, 60, 61, 150, 400, 900, 1700)])
+    with ob.Searcher(1) as s:
+        s.load_db(db)
+        tm = check(s, db, q, "blosum62", 10, 2, 10)
+        assert tm["launches"] >= 4 * 20            # four batches, each with its own scoring + top-r launches
