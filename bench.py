@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels", type=int, default=3, help="kernel mask (1|2 = default, 2 = 32-bit only)")
     ap.add_argument("--chunk-cols", type=int, default=0, help="residues per chunk (0 = library default)")
+    ap.add_argument("--window-mb", type=int, default=0, help="stream the database through two device windows of this size (experiments; 0 = resident)")
     ap.add_argument("--query-lengths", default="", help="comma-separated subset/alternative query lengths (experiments; default: the 20 standard lengths)")
     args = ap.parse_args()
     if args.query_lengths:
@@ -239,6 +240,8 @@ def main():
 
     s = ob.Searcher(devices=[local_rank])
     s.set_kernels(args.kernels)
+    if args.window_mb:
+        s.set_device_window(args.window_mb << 20)
     s.load_db(db, shard_rank=rank, shard_count=world, max_chunk_residues=args.chunk_cols)
     st = s.stats()
 

@@ -93,6 +93,12 @@ void osw_free(osw_ctx *ctx);
  * -k (arguments.c:113-117); 0 = default. */
 int osw_db_load(osw_ctx *ctx, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
                 int shard_rank, int shard_count, uint64_t max_chunk_residues);
+/* Device window for the database, the GPU meaning of the reference's -k ("maximum chunk size in
+ * FPGA (bytes)", arguments.c:113-117): when a GPU's share of the column stream is larger than
+ * `bytes`, it is not kept resident; every search streams it from pinned host memory through two
+ * windows of that size, the copy of the next segment overlapping the scoring of the current one.
+ * 0 (default) = keep the database resident.  Call before osw_db_load. */
+int osw_set_device_window(osw_ctx *ctx, uint64_t bytes);
 /* Copies the chunk streams (kept in pinned host memory by osw_db_load) to the GPUs again:
  * the host->device leg of a cold search, reference clEnqueueWriteBuffer HybridSearch.c:694-707.
  * bytes (nullable) receives the bytes copied. */

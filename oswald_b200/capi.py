@@ -36,6 +36,7 @@ SYMBOLS = {
     "osw_init": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
     "osw_free": (None, [C.c_void_p]),
     "osw_db_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64]),
+    "osw_set_device_window": (C.c_int, [C.c_void_p, C.c_uint64]),
     "osw_db_upload": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "osw_db_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "osw_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,

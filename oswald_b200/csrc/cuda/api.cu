@@ -33,6 +33,12 @@ struct DevState {
     int dev = -1, n_sms = 0;
     std::vector<LaunchRecord> trace;           // first-stage launches of the last search
     cudaStream_t st = nullptr, st2 = nullptr;      // st2: concurrent launch for very long chunks
+    cudaStream_t st_copy = nullptr;                // host -> window copies in streaming mode
+    bool streaming = false;                        // the column stream is not resident: two windows
+    uint8_t *d_win[2] = {nullptr, nullptr}; size_t win_bytes = 0;
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    uint8_t *d_stage = nullptr; size_t stage_cap = 0;         // sequences gathered for the 32-bit re-score (streaming mode)
+    uint64_t *d_task_off = nullptr; size_t task_off_cap = 0;
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // database shard
@@ -84,6 +90,7 @@ int grow_pinned(T **ptr, size_t *cap, size_t need) {
 void free_db(DevState &d) {
     cudaSetDevice(d.dev);
     cudaFree(d.d_pair); d.d_pair = nullptr;
+    cudaFree(d.d_win[0]); cudaFree(d.d_win[1]); d.d_win[0] = d.d_win[1] = nullptr; d.win_bytes = 0; d.streaming = false;
     if (d.h_pair) cudaFreeHost(d.h_pair);
     d.h_pair = nullptr;
     cudaFree(d.d_stream); cudaFree(d.d_chunks); cudaFree(d.d_canon); cudaFree(d.d_seq_off); cudaFree(d.d_seq_len);
@@ -98,8 +105,10 @@ void free_db(DevState &d) {
 int upload_db(DevState &d) {
     const osw_shard &s = d.shard;
     CK(cudaSetDevice(d.dev));
-    CK(cudaMemcpyAsync(d.d_stream, d.h_stream, s.stream_bytes, cudaMemcpyHostToDevice, d.st));
-    if (d.h_pair) CK(cudaMemcpyAsync(d.d_pair, d.h_pair, 2 * s.pair_cols, cudaMemcpyHostToDevice, d.st));
+    if (!d.streaming) {
+        CK(cudaMemcpyAsync(d.d_stream, d.h_stream, s.stream_bytes, cudaMemcpyHostToDevice, d.st));
+        if (d.h_pair && d.d_pair) CK(cudaMemcpyAsync(d.d_pair, d.h_pair, 2 * s.pair_cols, cudaMemcpyHostToDevice, d.st));
+    }
     CK(cudaMemcpyAsync(d.d_chunks, s.chunks, s.n_chunks * sizeof(osw_chunk), cudaMemcpyHostToDevice, d.st));
     CK(cudaMemcpyAsync(d.d_canon, s.canon, s.n_seqs * sizeof(uint32_t), cudaMemcpyHostToDevice, d.st));
     CK(cudaMemcpyAsync(d.d_seq_off, s.seq_off, s.n_seqs * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st));
@@ -117,6 +126,7 @@ struct osw_ctx {
     int n_dev = 0;
     DevState *devs = nullptr;
     int kernel_mask = OSW_K_DEFAULT;
+    uint64_t window_bytes = 0;         // osw_set_device_window
     bool db_loaded = false;
     uint64_t n_seqs_canon = 0;        // size of the whole canonical database
     uint64_t n_seqs_local = 0, residues_local = 0, chunks_local = 0;
@@ -191,7 +201,12 @@ extern "C" int osw_init(int n_devices, const int *devices, osw_ctx **out) {
             osw_free(c); return cuda_fail(e, "stream setup", __LINE__);
         }
         for (auto &ev : d.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) { osw_free(c); return cuda_fail(e, "cudaEventCreate", __LINE__); }
-        if ((e = cudaStreamCreateWithFlags(&d.st2, cudaStreamNonBlocking)) != cudaSuccess ||
+        if ((e = cudaStreamCreateWithFlags(&d.st_copy, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.ev_ready[0], cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.ev_ready[1], cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.ev_free[0], cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.ev_free[1], cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&d.st2, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming)) != cudaSuccess) {
             osw_free(c); return cuda_fail(e, "stream setup", __LINE__);
@@ -228,6 +243,9 @@ extern "C" void osw_free(osw_ctx *c) {
         if (d.h_cycles) cudaFreeHost(d.h_cycles);
         if (d.h_counts) cudaFreeHost(d.h_counts);
         for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
+        for (int k = 0; k < 2; ++k) { if (d.ev_ready[k]) cudaEventDestroy(d.ev_ready[k]); if (d.ev_free[k]) cudaEventDestroy(d.ev_free[k]); }
+        if (d.st_copy) cudaStreamDestroy(d.st_copy);
+        cudaFree(d.d_stage); cudaFree(d.d_task_off);
         if (d.ev_fork) cudaEventDestroy(d.ev_fork);
         if (d.ev_join) cudaEventDestroy(d.ev_join);
         if (d.st2) cudaStreamDestroy(d.st2);
@@ -241,6 +259,13 @@ extern "C" int osw_set_kernels(osw_ctx *c, int mask) {
     if (!c || !(mask & OSW_K_I32)) return OSW_E_ARG;   // the 32-bit stage is never optional
     if ((mask & OSW_K_TWO_TRACK) && (mask & OSW_K_PAIR_DB)) return OSW_E_ARG;
     c->kernel_mask = mask;
+    return OSW_OK;
+}
+
+extern "C" int osw_set_device_window(osw_ctx *c, uint64_t bytes) {
+    if (!c) return OSW_E_ARG;
+    if (bytes && bytes < (1u << 20)) bytes = 1u << 20;          // a window holds at least a few of the longest chunks
+    c->window_bytes = bytes;
     return OSW_OK;
 }
 
@@ -286,7 +311,14 @@ extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *
         d.h_stream = d.shard.stream; d.h_pair = d.shard.pair_stream;     // owned by DevState (freed in free_db)
         d.shard.stream = nullptr; d.shard.pair_stream = nullptr;
         const osw_shard &s = d.shard;
-        CK(cudaMalloc(&d.d_stream, s.stream_bytes ? s.stream_bytes : 1));
+        d.streaming = c->window_bytes && s.stream_bytes > c->window_bytes;
+        if (d.streaming) {
+            d.win_bytes = (size_t)c->window_bytes;
+            CK(cudaMalloc(&d.d_win[0], d.win_bytes));
+            CK(cudaMalloc(&d.d_win[1], d.win_bytes));
+        } else {
+            CK(cudaMalloc(&d.d_stream, s.stream_bytes ? s.stream_bytes : 1));
+        }
         CK(cudaMalloc(&d.d_chunks, (s.n_chunks ? s.n_chunks : 1) * sizeof(osw_chunk)));
         CK(cudaMalloc(&d.d_canon, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint32_t)));
         CK(cudaMalloc(&d.d_seq_off, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint64_t)));
@@ -423,15 +455,19 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
         // first pair-database search on this database: derive the pair stream from the plain one
         CK(cudaMallocHost(&d.h_pair, s.pair_cols ? 2 * s.pair_cols : 1));
         osw_shard_fill_pair(&s, d.h_stream, d.h_pair);
-        CK(cudaMalloc(&d.d_pair, s.pair_cols ? 2 * s.pair_cols : 1));
-        CK(cudaMemcpyAsync(d.d_pair, d.h_pair, 2 * s.pair_cols, cudaMemcpyHostToDevice, d.st));
+        if (!d.streaming) {
+            CK(cudaMalloc(&d.d_pair, s.pair_cols ? 2 * s.pair_cols : 1));
+            CK(cudaMemcpyAsync(d.d_pair, d.h_pair, 2 * s.pair_cols, cudaMemcpyHostToDevice, d.st));
+        }
     }
     if (use_u16 && N) {
-        uint64_t bound_col0 = 0;
+        uint64_t bound_col0 = 0, win_col0 = 0;
+        const uint8_t *win_ptr = nullptr;             // streaming mode: the device window holding the current segment
         auto launch = [&](const OswPass &ps, uint32_t first, uint32_t end, cudaStream_t st) -> int {
             if (slot >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
             U16Params up;
-            up.stream = d.d_stream; up.pair_stream = d.d_pair; up.chunks = d.d_chunks;
+            up.stream = win_ptr ? win_ptr : d.d_stream; up.pair_stream = win_ptr ? win_ptr : d.d_pair; up.stream_col0 = win_col0;
+            up.chunks = d.d_chunks;
             up.chunk_first = first; up.chunk_end = end;
             up.queries = d.d_queries; up.q_off = d.d_qoff; up.matrix = d.d_matrix;
             up.profile = d.d_profile[st == d.st2 ? 1 : 0];
@@ -455,7 +491,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
         // lead the descending list) go to a second, concurrent launch with one sequence per warp:
         // 32 lanes sweep the sequence's anti-diagonals (the intra-task path).
         uint32_t n_long = 0;
-        if (passes.size() == 1 && passes[0].G < 32 && wide.size() == 1) {
+        if (passes.size() == 1 && passes[0].G < 32 && wide.size() == 1 && !d.streaming) {
             const OswPass &ps = passes[0];
             const double cols_total = (double)(ps.pair_db ? s.pair_cols : s.n_residues);
             const double ideal_cycles = 2.0 * ps.G * ps.R * cols_total / (23.0 * d.n_sms);
@@ -482,21 +518,38 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
                 const uint64_t n = pd ? s.chunks[k].n_pair_cols : s.chunks[k].n_cols, al = pd ? 64 : OSW_CHUNK_ALIGN;
                 return chunk_begin(k) + (n + al - 1) / al * al;
             };
-            uint32_t seg_first = 0;
+            const uint64_t bpc = pd ? 2 : 1;                               // bytes per column of the stream in use
+            const uint8_t *h_src = pd ? d.h_pair : d.h_stream;
+            const uint64_t win_cols = d.streaming ? d.win_bytes / bpc : ~0ull;
+            const bool bounded = d.d_bound && passes.size() > 1;
+            uint32_t seg_first = 0, seg_no = 0;
             while (seg_first < s.n_chunks) {
                 uint32_t seg_end = s.n_chunks;
-                if (d.d_bound && passes.size() > 1) {
+                if (bounded || d.streaming) {
+                    const uint64_t cap = std::min<uint64_t>(bounded ? d.bound_cap : ~0ull, win_cols);
                     seg_end = seg_first + 1;
-                    while (seg_end < s.n_chunks && chunk_end(seg_first) - chunk_begin(seg_end) <= d.bound_cap) ++seg_end;
-                    bound_col0 = chunk_begin(seg_end - 1);
-                    if (chunk_end(seg_first) - bound_col0 > d.bound_cap) {
-                        snprintf(g_err, sizeof g_err, "a chunk is larger than the bottom-row buffer");
+                    while (seg_end < s.n_chunks && chunk_end(seg_first) - chunk_begin(seg_end) <= cap) ++seg_end;
+                    const uint64_t seg_col0 = chunk_begin(seg_end - 1);
+                    if (chunk_end(seg_first) - seg_col0 > cap) {
+                        snprintf(g_err, sizeof g_err, "a chunk is larger than the device window / bottom-row buffer");
                         return OSW_E_NOMEM;
+                    }
+                    bound_col0 = seg_col0;
+                    if (d.streaming) {
+                        // copy the segment into the free window while the previous segment is being scored
+                        const int w = (int)(seg_no & 1);
+                        CK(cudaStreamWaitEvent(d.st_copy, d.ev_free[w], 0));
+                        CK(cudaMemcpyAsync(d.d_win[w], h_src + seg_col0 * bpc, (chunk_end(seg_first) - seg_col0) * bpc,
+                                           cudaMemcpyHostToDevice, d.st_copy));
+                        CK(cudaEventRecord(d.ev_ready[w], d.st_copy));
+                        CK(cudaStreamWaitEvent(d.st, d.ev_ready[w], 0));
+                        win_ptr = d.d_win[w]; win_col0 = seg_col0;
                     }
                 }
                 for (const OswPass &ps : passes)
                     if ((rc = launch(ps, seg_first, seg_end, d.st)) != OSW_OK) return rc;
-                seg_first = seg_end;
+                if (d.streaming) CK(cudaEventRecord(d.ev_free[seg_no & 1], d.st));
+                seg_first = seg_end; ++seg_no;
             }
         }
         CK(cudaEventRecord(d.ev[1], d.st));
@@ -591,7 +644,7 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
         const uint64_t N = s.n_seqs;
         CK(cudaSetDevice(d.dev));
         I32Params ip;
-        ip.stream = d.d_stream; ip.seq_off = d.d_seq_off; ip.seq_len = d.d_seq_len;
+        ip.stream = d.d_stream; ip.seq_off = d.d_seq_off; ip.seq_len = d.d_seq_len; ip.task_off = nullptr;
         ip.queries = d.d_queries; ip.q_off = d.d_qoff; ip.matrix = d.d_matrix;
         ip.n_seqs = N; ip.scores = d.d_scores; ip.scratch = d.d_scratch; ip.max_len = s.max_len ? s.max_len : 1;
         ip.gap_open_extend = go + ge; ip.gap_extend = ge; ip.task_counter = d.d_task_counter;
@@ -615,11 +668,28 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
             if (n_flag) {
                 int rc2 = need_scratch();
                 if (rc2 != OSW_OK) return rc2;
+                if (d.streaming) {
+                    // the stream is not resident: gather the flagged sequences from the pinned host copy
+                    std::vector<uint2> hp(n_flag);
+                    CK(cudaMemcpy(hp.data(), d.d_pairs, (size_t)n_flag * sizeof(uint2), cudaMemcpyDeviceToHost));
+                    std::vector<uint64_t> off(n_flag);
+                    uint64_t total = 0;
+                    for (uint32_t k = 0; k < n_flag; ++k) { off[k] = total; total += s.seq_len[hp[k].y]; }
+                    std::vector<uint8_t> stage(total ? total : 1);
+                    for (uint32_t k = 0; k < n_flag; ++k)
+                        memcpy(stage.data() + off[k], d.h_stream + s.seq_off[hp[k].y], s.seq_len[hp[k].y]);
+                    if ((rc2 = grow(&d.d_stage, &d.stage_cap, stage.size())) != OSW_OK) return rc2;
+                    if ((rc2 = grow(&d.d_task_off, &d.task_off_cap, (size_t)n_flag)) != OSW_OK) return rc2;
+                    CK(cudaMemcpy(d.d_stage, stage.data(), stage.size(), cudaMemcpyHostToDevice));
+                    CK(cudaMemcpy(d.d_task_off, off.data(), (size_t)n_flag * sizeof(uint64_t), cudaMemcpyHostToDevice));
+                    ip.stream = d.d_stage; ip.task_off = d.d_task_off;
+                }
                 ip.pairs = d.d_pairs; ip.n_tasks = n_flag;
                 osw_launch_i32(ip, (int)std::min<uint64_t>((uint64_t)i32_blocks, ((uint64_t)n_flag + 7) / 8), d.st);
                 ++launches;
             }
         } else if (N) {
+            if (d.streaming) { snprintf(g_err, sizeof g_err, "the 32-bit-only mode needs a resident database"); return OSW_E_STATE; }
             int rc2 = need_scratch();
             if (rc2 != OSW_OK) return rc2;
             ip.pairs = nullptr; ip.n_tasks = (uint64_t)nq * N;

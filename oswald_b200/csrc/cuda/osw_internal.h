@@ -17,6 +17,7 @@ struct I32Params {
     const uint32_t *q_off;       // [nq+1]
     const int8_t   *matrix;      // [24*32]
     const uint2    *pairs;       // (query, local sequence) list, or nullptr = all pairs
+    const uint64_t *task_off;    // optional: stream offset of each task's sequence (replaces seq_off[s]; staged re-score)
     uint64_t        n_tasks;     // pairs in the list, or nq*n_seqs
     uint64_t        n_seqs;
     int32_t        *scores;      // [nq][n_seqs]
@@ -59,8 +60,9 @@ struct OswPass {
 extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes, int mode, int min_g);
 
 struct U16Params {
-    const uint8_t   *stream;
-    const uint8_t   *pair_stream; // two bytes per column (pair-database mode)
+    const uint8_t   *stream;      // the columns [stream_col0, ...) of the shard's stream (all of it, or a window)
+    const uint8_t   *pair_stream; // two bytes per column (pair-database mode); same window convention
+    uint64_t         stream_col0;
     const osw_chunk *chunks;     // descending-length order
     uint32_t         chunk_first, chunk_end;   // the launch works on chunks [chunk_first, chunk_end)
     const uint8_t   *queries;    // all queries back to back (codes)

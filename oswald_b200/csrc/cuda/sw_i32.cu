@@ -42,7 +42,7 @@ sw_i32_kernel(I32Params p) {
         else { q = (uint32_t)(task / p.n_seqs); s = (uint32_t)(task % p.n_seqs); }
         const uint8_t *a = p.queries + p.q_off[q];
         const int m = (int)(p.q_off[q + 1] - p.q_off[q]);
-        const uint8_t *b = p.stream + p.seq_off[s];
+        const uint8_t *b = p.stream + (p.task_off ? p.task_off[task] : p.seq_off[s]);
         const int n = (int)p.seq_len[s];
         int best = 0;
         const int n_pass = (m + ROWS_PER_PASS - 1) / ROWS_PER_PASS;

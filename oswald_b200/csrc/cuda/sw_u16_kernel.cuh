@@ -257,7 +257,7 @@ sw_u16_kernel(const KArgs a) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
         const uint32_t n_blocks = (steps + 31) / 32;
-        const uint8_t *col_src = PD ? p.pair_stream + 2 * (col0 + t * EPL) : p.stream + col0 + t * EPL;
+        const uint8_t *col_src = PD ? p.pair_stream + 2 * (col0 - p.stream_col0 + t * EPL) : p.stream + (col0 - p.stream_col0) + t * EPL;
         const uint2 *bnd_src = multi_in ? p.bound + (col0 - p.bound_col0) + t * EPL : nullptr;
         constexpr uint32_t COL_ALIGN = PD ? 64 : OSW_CHUNK_ALIGN;
         const uint32_t cols_padded = have ? (n_cols + COL_ALIGN - 1) / COL_ALIGN * COL_ALIGN : 0;

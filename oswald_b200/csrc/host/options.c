@@ -26,7 +26,7 @@ static struct argp_option options[] = {
     {"gap_open", 'g', "<integer>", 0, "Gap open penalty (default: 10).", 3},
     {"gap_extend", 'e', "<integer>", 0, "Gap extend penalty (default: 2).", 3},
     {"top", 'r', "<integer>", 0, "Number of scores to show (default: 10).", 3},
-    {"max_chunk_size", 'k', "<integer>", 0, "Maximum chunk size on the GPU (residues per chunk, default: 134217728; chunks never exceed the built-in work-unit size).", 3},
+    {"max_chunk_size", 'k', "<integer>", 0, "Maximum size of the database on a GPU at a time (bytes): a larger database is streamed from host memory through two windows of this size while it is scored. Default: keep the database resident (the reference's default, 134217728, applies only when -k is given).", 3},
     {"num_fpgas", 'f', "<integer>", 0, "Number of GPUs (default: 1; the reference's number of FPGAs).", 3},
     {"cpu_threads", 'c', "<integer>", 0, "Number of host threads for preprocessing (default: 4).", 3},
     {"execution_mode", 'm', "<integer>", 0, "Accepted for compatibility (FPGA/hybrid mode); ignored.", 3},
@@ -81,6 +81,7 @@ static error_t parse_opt(int key, char *arg, struct argp_state *state) {
             long v = atol(arg);
             if (v <= 0) argp_failure(state, 1, 0, "The chunk size must be greater than 0.");
             o->max_chunk_size = (unsigned long)v;
+            o->max_chunk_size_given = 1;
             break;
         }
         case 'p': o->test_db_percentage = atof(arg); break;

@@ -32,6 +32,7 @@ typedef struct osw_options {
     int         open_gap, extend_gap;   /* -g -e */
     unsigned long top;                  /* -r */
     unsigned long max_chunk_size;       /* -k */
+    int         max_chunk_size_given;   /* -k was on the command line */
     unsigned    num_devices;            /* -f: number of GPUs (was: FPGAs) */
     int         cpu_threads;            /* -c: host threads for preprocessing */
     /* accepted for command-line compatibility, no effect on a GPU: */

@@ -69,7 +69,8 @@ int gpu_search(const osw_options *opt) {
         return 1;
     }
     PHASE("osw_init");
-    if ((rc = osw_db_load(ctx, db.residues, db.offsets, db.n_seqs, 0, 1, opt->max_chunk_size)) != OSW_OK) {
+    if (opt->max_chunk_size_given) osw_set_device_window(ctx, opt->max_chunk_size);      /* -k, arguments.c:113-117 */
+    if ((rc = osw_db_load(ctx, db.residues, db.offsets, db.n_seqs, 0, 1, 0)) != OSW_OK) {
         printf("OSWALD: cannot load the database on the GPU(s): %s (%s).\n", osw_strerror(rc), osw_last_error());
         osw_free(ctx);
         return 1;
@@ -119,7 +120,8 @@ int gpu_search(const osw_options *opt) {
     printf("Number of GPUs:\t\t\t%u\n", opt->num_devices);
     printf("Kernel launches:\t\t%lu\n", (unsigned long)tm.launches);
     printf("Pairs re-scored at 32 bit:\t%lu\n", (unsigned long)tm.rescored_pairs);
-    printf("Max. chunk size on GPU:\t\t%lu residues\n", opt->max_chunk_size);
+    if (opt->max_chunk_size_given) printf("Max. chunk size on GPU:\t\t%lu bytes (database streamed through two windows)\n", opt->max_chunk_size);
+    else printf("Max. chunk size on GPU:\t\tdatabase resident\n");
 
     for (size_t k = 0; k < n_print; ++k) free(titles[k]);
     free(titles); free(idx); free(hits); free(n_hits); free(all); free(a); free(a_disp); free(qperm);

@@ -174,6 +174,10 @@ class Searcher:
     def set_kernels(self, mask):
         capi.check(self._L.osw_set_kernels(self._ctx, mask), "osw_set_kernels")
 
+    def set_device_window(self, n_bytes):
+        """Stream databases larger than n_bytes per GPU through two device windows (0 = resident)."""
+        capi.check(self._L.osw_set_device_window(self._ctx, n_bytes), "osw_set_device_window")
+
     def load_db(self, db, shard_rank=0, shard_count=1, max_chunk_residues=0):
         capi.check(self._L.osw_db_load(self._ctx, _vp(db.residues), _vp(db.offsets), db.n_seqs,
                                        shard_rank, shard_count, max_chunk_residues), "osw_db_load")

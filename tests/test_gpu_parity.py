@@ -225,7 +225,8 @@ def test_cli_report_matches_the_reference(built, tmp_path):
         subprocess.run([cli, "-O", "preprocess", "-i", "db.fasta", "-o", "db"], cwd=tmp_path, check=True)
         for run in meta["runs"][:3]:
             out = subprocess.run([cli, "-O", "search", "-q", "q.fasta", "-d", "db", "-s", run["matrix"], "-g", str(run["gap_open"]),
-                                  "-e", str(run["gap_extend"]), "-r", str(meta["top"]), "--dump-scores", "dump.bin"],
+                                  "-e", str(run["gap_extend"]), "-r", str(meta["top"]), "--dump-scores", "dump.bin"]
+                                 + (["-k", "1048576"] if run is meta["runs"][0] else []),
                                  cwd=tmp_path, check=True, capture_output=True, text=True).stdout
             blocks = out.split("Query no.")[1:]
             assert len(blocks) == len(run["hits"])
@@ -346,3 +347,28 @@ def test_query_batches(built, monkeypatch):
         s.load_db(db)
         tm = check(s, db, q, "blosum62", 10, 2, 10)
         assert tm["launches"] >= 4 * 20            # four batches, each with its own scoring + top-r launches
+
+
+def test_streamed_database_windows(built):
+    """osw_set_device_window: the column stream is not resident but copied segment by segment
+    through two device windows (the reference's -k); results, overflow re-score included, are
+    the same."""
+    rng = np.random.default_rng(404)
+    W = np.uint8(19)
+    seqs = rand_seqs(rng, 9000, 1, 600) + [AA[rng.integers(0, 20, size=n)] for n in (30000, 65535)] + [np.full(6000, W, dtype=np.uint8)]
+    q_sets = [[AA[rng.integers(0, 20, size=m)] for m in (144, 189, 222, 1500, 2900)],
+              [AA[rng.integers(0, 20, size=700)]],
+              [np.full(5400, W, dtype=np.uint8), AA[rng.integers(0, 20, size=100)]]]         # 70 200 > 16 bits: staged re-score
+    db = make_db(seqs)
+    assert db.n_residues > 2.5 * (1 << 20)
+    with ob.Searcher(1) as s:
+        s.set_device_window(1 << 20)
+        s.load_db(db)
+        for qs in q_sets:
+            q = ob.Queries.from_list(qs)
+            for mode in MODES.values():
+                tm = check(s, db, q, "pam30", 9, 1, 10, mask=mode)
+        assert tm["rescored_pairs"] >= 1
+        s.set_kernels(capi.OSW_K_I32)
+        with pytest.raises(capi.OswError):
+            s.search(q, ob.matrix("pam30"), 9, 1, top=5)
