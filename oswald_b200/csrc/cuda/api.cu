@@ -32,7 +32,7 @@ struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; u
 struct DevState {
     int dev = -1, n_sms = 0;
     std::vector<LaunchRecord> trace;           // first-stage launches of the last search
-    cudaStream_t st = nullptr, st2 = nullptr;      // st2: concurrent launch for very long chunks
+    cudaStream_t st = nullptr;
     cudaStream_t st_copy = nullptr;                // host -> window copies in streaming mode
     bool streaming = false;                        // the column stream is not resident: two windows
     uint8_t *d_win[2] = {nullptr, nullptr}; size_t win_bytes = 0;
@@ -40,12 +40,11 @@ struct DevState {
     uint8_t *d_stage = nullptr; size_t stage_cap = 0;         // sequences gathered for the 32-bit re-score (streaming mode)
     uint64_t *d_task_off = nullptr; size_t task_off_cap = 0;
     cudaEvent_t ev[6] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // database shard
     osw_shard shard = {};
     uint8_t *h_stream = nullptr;               // pinned copy of shard.stream (source of re-uploads)
     uint8_t *h_pair = nullptr, *d_pair = nullptr;   // pair stream (pinned host copy, device)
-    uint8_t *d_stream = nullptr; osw_chunk *d_chunks = nullptr; uint32_t *d_canon = nullptr;
+    uint8_t *d_stream = nullptr; osw_chunk *d_chunks = nullptr, *d_pair_chunks = nullptr; uint32_t *d_canon = nullptr;
     uint64_t *d_seq_off = nullptr; uint32_t *d_seq_len = nullptr;
     // per-search buffers (grown on demand)
     int32_t *d_scores = nullptr; size_t scores_cap = 0;
@@ -54,7 +53,7 @@ struct DevState {
     int8_t *d_matrix = nullptr;
     int2 *d_scratch = nullptr; size_t scratch_cap = 0;
     uint2 *d_bound = nullptr; size_t bound_cap = 0;   // bottom rows handed from pass to pass (in place), one segment of chunks at a time
-    unsigned char *d_profile[2] = {nullptr, nullptr};   // profile table images, one per stream
+    unsigned char *d_profile = nullptr;        // the current pass's profile table image
     uint2 *d_pairs = nullptr; uint32_t pairs_cap = 0;
     uint32_t *d_counters = nullptr;            // [0] flagged count, [1..] chunk counters per launch
     unsigned long long *d_task_counter = nullptr;   // [0] i32 queue, [1] n_tasks mirror
@@ -93,9 +92,9 @@ void free_db(DevState &d) {
     cudaFree(d.d_win[0]); cudaFree(d.d_win[1]); d.d_win[0] = d.d_win[1] = nullptr; d.win_bytes = 0; d.streaming = false;
     if (d.h_pair) cudaFreeHost(d.h_pair);
     d.h_pair = nullptr;
-    cudaFree(d.d_stream); cudaFree(d.d_chunks); cudaFree(d.d_canon); cudaFree(d.d_seq_off); cudaFree(d.d_seq_len);
+    cudaFree(d.d_stream); cudaFree(d.d_chunks); cudaFree(d.d_pair_chunks); cudaFree(d.d_canon); cudaFree(d.d_seq_off); cudaFree(d.d_seq_len);
     cudaFree(d.d_bound); d.bound_cap = 0;
-    d.d_stream = nullptr; d.d_chunks = nullptr; d.d_canon = nullptr; d.d_seq_off = nullptr; d.d_seq_len = nullptr;
+    d.d_stream = nullptr; d.d_chunks = nullptr; d.d_pair_chunks = nullptr; d.d_canon = nullptr; d.d_seq_off = nullptr; d.d_seq_len = nullptr;
     d.d_bound = nullptr;
     if (d.h_stream) cudaFreeHost(d.h_stream);
     d.h_stream = nullptr;
@@ -110,6 +109,7 @@ int upload_db(DevState &d) {
         if (d.h_pair && d.d_pair) CK(cudaMemcpyAsync(d.d_pair, d.h_pair, 2 * s.pair_cols, cudaMemcpyHostToDevice, d.st));
     }
     CK(cudaMemcpyAsync(d.d_chunks, s.chunks, s.n_chunks * sizeof(osw_chunk), cudaMemcpyHostToDevice, d.st));
+    CK(cudaMemcpyAsync(d.d_pair_chunks, s.pair_chunks, s.n_pair_chunks * sizeof(osw_chunk), cudaMemcpyHostToDevice, d.st));
     CK(cudaMemcpyAsync(d.d_canon, s.canon, s.n_seqs * sizeof(uint32_t), cudaMemcpyHostToDevice, d.st));
     CK(cudaMemcpyAsync(d.d_seq_off, s.seq_off, s.n_seqs * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st));
     CK(cudaMemcpyAsync(d.d_seq_len, s.seq_len, s.n_seqs * sizeof(uint32_t), cudaMemcpyHostToDevice, d.st));
@@ -205,15 +205,11 @@ extern "C" int osw_init(int n_devices, const int *devices, osw_ctx **out) {
             (e = cudaEventCreateWithFlags(&d.ev_ready[0], cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&d.ev_ready[1], cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&d.ev_free[0], cudaEventDisableTiming)) != cudaSuccess ||
-            (e = cudaEventCreateWithFlags(&d.ev_free[1], cudaEventDisableTiming)) != cudaSuccess ||
-            (e = cudaStreamCreateWithFlags(&d.st2, cudaStreamNonBlocking)) != cudaSuccess ||
-            (e = cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
-            (e = cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming)) != cudaSuccess) {
+            (e = cudaEventCreateWithFlags(&d.ev_free[1], cudaEventDisableTiming)) != cudaSuccess) {
             osw_free(c); return cuda_fail(e, "stream setup", __LINE__);
         }
         if ((e = cudaMalloc(&d.d_matrix, 24 * 32)) != cudaSuccess ||
-            (e = cudaMalloc(&d.d_profile[0], OSW_PROFILE_BYTES)) != cudaSuccess ||
-            (e = cudaMalloc(&d.d_profile[1], OSW_PROFILE_BYTES)) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_profile, OSW_PROFILE_BYTES)) != cudaSuccess ||
             (e = cudaMalloc(&d.d_counters, (1 + MAX_LAUNCH_SLOTS) * sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_task_counter, 2 * sizeof(unsigned long long))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_cycles, MAX_LAUNCH_SLOTS * sizeof(unsigned long long))) != cudaSuccess ||
@@ -235,7 +231,7 @@ extern "C" void osw_free(osw_ctx *c) {
         if (d.st) cudaStreamSynchronize(d.st);
         free_db(d);
         cudaFree(d.d_scores); cudaFree(d.d_queries); cudaFree(d.d_qoff); cudaFree(d.d_matrix); cudaFree(d.d_scratch);
-        cudaFree(d.d_profile[0]); cudaFree(d.d_profile[1]);
+        cudaFree(d.d_profile);
         cudaFree(d.d_pairs); cudaFree(d.d_counters); cudaFree(d.d_task_counter); cudaFree(d.d_cycles);
         cudaFree(d.topr.hist); cudaFree(d.topr.prefix); cudaFree(d.topr.remaining); cudaFree(d.topr.out_count); cudaFree(d.topr.out_keys);
         if (d.h_keys) cudaFreeHost(d.h_keys);
@@ -246,9 +242,6 @@ extern "C" void osw_free(osw_ctx *c) {
         for (int k = 0; k < 2; ++k) { if (d.ev_ready[k]) cudaEventDestroy(d.ev_ready[k]); if (d.ev_free[k]) cudaEventDestroy(d.ev_free[k]); }
         if (d.st_copy) cudaStreamDestroy(d.st_copy);
         cudaFree(d.d_stage); cudaFree(d.d_task_off);
-        if (d.ev_fork) cudaEventDestroy(d.ev_fork);
-        if (d.ev_join) cudaEventDestroy(d.ev_join);
-        if (d.st2) cudaStreamDestroy(d.st2);
         if (d.st) cudaStreamDestroy(d.st);
     }
     delete[] c->devs;
@@ -320,6 +313,7 @@ extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *
             CK(cudaMalloc(&d.d_stream, s.stream_bytes ? s.stream_bytes : 1));
         }
         CK(cudaMalloc(&d.d_chunks, (s.n_chunks ? s.n_chunks : 1) * sizeof(osw_chunk)));
+        CK(cudaMalloc(&d.d_pair_chunks, (s.n_pair_chunks ? s.n_pair_chunks : 1) * sizeof(osw_chunk)));
         CK(cudaMalloc(&d.d_canon, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint32_t)));
         CK(cudaMalloc(&d.d_seq_off, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint64_t)));
         CK(cudaMalloc(&d.d_seq_len, (s.n_seqs ? s.n_seqs : 1) * sizeof(uint32_t)));
@@ -389,7 +383,7 @@ constexpr int MAX_PASSES = 2048;
 
 int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32_t *q_off, int nq,
                    const int8_t *matrix, int go, int ge, uint32_t top_r, bool want_all,
-                   const std::vector<OswPass> &passes, const std::vector<OswPass> &wide,
+                   const std::vector<OswPass> &passes,
                    uint32_t *n_launch_slots, uint64_t *launches, uint64_t *padded_cells) {
     const osw_shard &s = d.shard;
     const uint64_t N = s.n_seqs;
@@ -404,9 +398,9 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
         cudaFree(d.topr.hist); cudaFree(d.topr.prefix); cudaFree(d.topr.remaining); cudaFree(d.topr.out_count); cudaFree(d.topr.out_keys);
         d.topr = TopRWork(); d.topr_nq = 0; d.topr_r = 0;
         const int qn = std::max(nq, d.topr_nq); const uint32_t rn = std::max(r, std::max(d.topr_r, 1u));
-        CK(cudaMalloc(&d.topr.hist, (size_t)qn * 256 * sizeof(uint32_t)));
-        CK(cudaMalloc(&d.topr.prefix, (size_t)qn * sizeof(unsigned long long)));
-        CK(cudaMalloc(&d.topr.remaining, (size_t)qn * sizeof(uint32_t)));
+        CK(cudaMalloc(&d.topr.hist, (size_t)qn * 8 * 256 * sizeof(uint32_t)));
+        CK(cudaMalloc(&d.topr.prefix, (size_t)qn * 8 * sizeof(unsigned long long)));
+        CK(cudaMalloc(&d.topr.remaining, (size_t)qn * 8 * sizeof(uint32_t)));
         CK(cudaMalloc(&d.topr.out_count, (size_t)qn * sizeof(uint32_t)));
         CK(cudaMalloc(&d.topr.out_keys, (size_t)qn * rn * sizeof(unsigned long long)));
         d.topr_nq = qn; d.topr_r = rn;
@@ -463,72 +457,56 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
     if (use_u16 && N) {
         uint64_t bound_col0 = 0, win_col0 = 0;
         const uint8_t *win_ptr = nullptr;             // streaming mode: the device window holding the current segment
-        auto launch = [&](const OswPass &ps, uint32_t first, uint32_t end, cudaStream_t st) -> int {
+        // pair-database passes walk the pair directory and the pair stream, the others the plain ones
+        const bool pd = !passes.empty() && passes[0].pair_db;
+        const osw_chunk *dir = pd ? s.pair_chunks : s.chunks;
+        const uint32_t n_dir = pd ? s.n_pair_chunks : s.n_chunks;
+        auto chunk_cols = [&](uint32_t k) -> uint64_t { return pd ? dir[k].n_pair_cols : dir[k].n_cols; };
+        auto chunk_begin = [&](uint32_t k) -> uint64_t { return pd ? dir[k].pair_off : dir[k].stream_off; };
+        auto chunk_end = [&](uint32_t k) -> uint64_t {
+            const uint64_t al = pd ? 64 : OSW_CHUNK_ALIGN;
+            return chunk_begin(k) + (chunk_cols(k) + al - 1) / al * al;
+        };
+        auto launch = [&](const OswPass &ps, uint32_t first, uint32_t end) -> int {
             if (slot >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
             U16Params up;
             up.stream = win_ptr ? win_ptr : d.d_stream; up.pair_stream = win_ptr ? win_ptr : d.d_pair; up.stream_col0 = win_col0;
-            up.chunks = d.d_chunks;
-            up.chunk_first = first; up.chunk_end = end;
+            up.chunks = pd ? d.d_pair_chunks : d.d_chunks;
+            up.chunk_first = first; up.chunk_end = end; up.static_first = 0;
             up.queries = d.d_queries; up.q_off = d.d_qoff; up.matrix = d.d_matrix;
-            up.profile = d.d_profile[st == d.st2 ? 1 : 0];
+            up.profile = d.d_profile;
             up.scores = d.d_scores; up.n_seqs = N;
             up.bound = d.d_bound; up.bound_col0 = bound_col0;
             up.gap_open_extend = go + ge; up.gap_extend = ge;
             up.chunk_counter = d.d_counters + 1 + slot;
             up.cycle_acc = d.d_cycles + slot;
-            int rc2 = osw_launch_u16(up, ps, d.n_sms, st);
+            int rc2 = osw_launch_u16(up, ps, d.n_sms, d.st);
             if (rc2 != OSW_OK) { cuda_fail(cudaGetLastError(), "sw_u16 launch", __LINE__); return rc2; }
             uint64_t cols = 0;
-            if (first == 0 && end == s.n_chunks) cols = ps.pair_db ? s.pair_cols : s.n_residues;
-            else for (uint32_t k = first; k < end; ++k) cols += ps.pair_db ? s.chunks[k].n_pair_cols : s.chunks[k].n_cols;
+            if (first == 0 && end == n_dir) cols = pd ? s.pair_cols : s.n_residues;
+            else for (uint32_t k = first; k < end; ++k) cols += chunk_cols(k);
             d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols});
             ++slot; *launches += 2;               // profile_build_kernel + sw_u16_kernel
             *padded_cells += (uint64_t)ps.G * ps.R * 2 * cols;
             return OSW_OK;
         };
-        // A narrow plan (G < 32: several sequences per warp) leaves a very long sequence to a few
-        // lanes, and that chunk's latency would outlast the rest of the launch.  Such chunks (they
-        // lead the descending list) go to a second, concurrent launch with one sequence per warp:
-        // 32 lanes sweep the sequence's anti-diagonals (the intra-task path).
-        uint32_t n_long = 0;
-        if (passes.size() == 1 && passes[0].G < 32 && wide.size() == 1 && !d.streaming) {
-            const OswPass &ps = passes[0];
-            const double cols_total = (double)(ps.pair_db ? s.pair_cols : s.n_residues);
-            const double ideal_cycles = 2.0 * ps.G * ps.R * cols_total / (23.0 * d.n_sms);
-            const double step_latency = ps.R / 2.0 * 14.0 + 60.0;
-            const double limit = std::max(512.0, 0.5 * ideal_cycles / step_latency);
-            while (n_long < s.n_chunks && (double)(ps.pair_db ? s.chunks[n_long].n_pair_cols : s.chunks[n_long].n_cols) > limit) ++n_long;
-        }
-        if (n_long) {
-            CK(cudaEventRecord(d.ev_fork, d.st));
-            CK(cudaStreamWaitEvent(d.st2, d.ev_fork, 0));
-            if ((rc = launch(wide[0], 0, n_long, d.st2)) != OSW_OK) return rc;
-            if (n_long < s.n_chunks && (rc = launch(passes[0], n_long, s.n_chunks, d.st)) != OSW_OK) return rc;
-            CK(cudaEventRecord(d.ev_join, d.st2));
-            CK(cudaStreamWaitEvent(d.st, d.ev_join, 0));
-        } else {
+        {
             // One launch per pass, in order: a pass reads the bottom row the previous one parked (in
             // place: a warp writes a chunk's columns behind the ones it still has to read).  With
             // several passes the chunk list is cut into segments whose bottom rows fit the buffer;
             // chunks are stored back to back in ascending order, so a range of the (descending)
             // directory is one contiguous stretch of the stream.
-            const bool pd = !passes.empty() && passes[0].pair_db;
-            auto chunk_begin = [&](uint32_t k) { return pd ? s.chunks[k].pair_off : s.chunks[k].stream_off; };
-            auto chunk_end = [&](uint32_t k) {
-                const uint64_t n = pd ? s.chunks[k].n_pair_cols : s.chunks[k].n_cols, al = pd ? 64 : OSW_CHUNK_ALIGN;
-                return chunk_begin(k) + (n + al - 1) / al * al;
-            };
             const uint64_t bpc = pd ? 2 : 1;                               // bytes per column of the stream in use
             const uint8_t *h_src = pd ? d.h_pair : d.h_stream;
             const uint64_t win_cols = d.streaming ? d.win_bytes / bpc : ~0ull;
             const bool bounded = d.d_bound && passes.size() > 1;
             uint32_t seg_first = 0, seg_no = 0;
-            while (seg_first < s.n_chunks) {
-                uint32_t seg_end = s.n_chunks;
+            while (seg_first < n_dir) {
+                uint32_t seg_end = n_dir;
                 if (bounded || d.streaming) {
                     const uint64_t cap = std::min<uint64_t>(bounded ? d.bound_cap : ~0ull, win_cols);
                     seg_end = seg_first + 1;
-                    while (seg_end < s.n_chunks && chunk_end(seg_first) - chunk_begin(seg_end) <= cap) ++seg_end;
+                    while (seg_end < n_dir && chunk_end(seg_first) - chunk_begin(seg_end) <= cap) ++seg_end;
                     const uint64_t seg_col0 = chunk_begin(seg_end - 1);
                     if (chunk_end(seg_first) - seg_col0 > cap) {
                         snprintf(g_err, sizeof g_err, "a chunk is larger than the device window / bottom-row buffer");
@@ -547,7 +525,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
                     }
                 }
                 for (const OswPass &ps : passes)
-                    if ((rc = launch(ps, seg_first, seg_end, d.st)) != OSW_OK) return rc;
+                    if ((rc = launch(ps, seg_first, seg_end)) != OSW_OK) return rc;
                 if (d.streaming) CK(cudaEventRecord(d.ev_free[seg_no & 1], d.st));
                 seg_first = seg_end; ++seg_no;
             }
@@ -611,20 +589,46 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
                         const int8_t *matrix, int go, int ge, int top_r,
                         osw_hit *hits, uint32_t *n_hits, int32_t *all_scores, osw_timing *timing) {
     const double t_wall0 = now_ms();
-    std::vector<OswPass> passes, wide;
+    std::vector<OswPass> passes;
     if (c->kernel_mask & OSW_K_U16) {
         std::vector<uint32_t> q_len((size_t)nq);
         for (int q = 0; q < nq; ++q) q_len[q] = q_off[q + 1] - q_off[q];
         passes.resize(MAX_PASSES);
         const int mode = (c->kernel_mask & OSW_K_PAIR_DB) ? OSW_PLAN_PAIR_DB : (c->kernel_mask & OSW_K_TWO_TRACK) ? OSW_PLAN_TWO_TRACK : OSW_PLAN_AUTO;
-        const int n_pass = osw_plan_passes(q_len.data(), nq, passes.data(), MAX_PASSES, mode, 4);
+        int n_pass = osw_plan_passes(q_len.data(), nq, passes.data(), MAX_PASSES, mode, 4);
         if (n_pass < 0) { snprintf(g_err, sizeof g_err, "the queries need more than %d passes", MAX_PASSES); return OSW_E_ARG; }
-        passes.resize((size_t)n_pass);
-        if (n_pass == 1 && passes[0].G < 32) {        // one-sequence-per-warp variant of the same plan, for very long sequences
-            wide.resize(4);
-            const int n_wide = osw_plan_passes(q_len.data(), nq, wide.data(), 4, passes[0].pair_db ? OSW_PLAN_PAIR_DB : OSW_PLAN_TWO_TRACK, 32);
-            wide.resize(n_wide == 1 ? 1 : 0);
+        if (n_pass == 1 && passes[0].G < 32) {
+            // The planner picked the geometry with the fewest padded rows.  That is the fastest one
+            // when the launch is bound by the DPX pipe; on a small database the launch lasts as long
+            // as its longest chunk (one dependent step per column, and a step takes longer the more
+            // rows a lane holds), and a wider array with fewer rows per lane finishes sooner despite
+            // its padding.  Estimate both terms for every group width and keep the best plan.
+            const DevState &d0 = c->devs[0];
+            const osw_shard &s0 = d0.shard;
+            const bool pd = passes[0].pair_db != 0;
+            const double cols = (double)(pd ? s0.pair_cols : s0.n_residues);
+            const double longest = !(pd ? s0.n_pair_chunks : s0.n_chunks) ? 0.0 : (double)(pd ? s0.pair_chunks[0].n_pair_cols : s0.chunks[0].n_cols);
+            // Measured on B200 (profiles/r1_ncu_summary.md, "small databases"): all SMs busy, a pass
+            // sustains 23 padded cell updates per SM-cycle (17.5 in pair-database mode) at R = 40, less
+            // with few rows per lane (about 5 rows' worth of per-step bookkeeping); a step of the
+            // longest chunk's warp takes about 230 + 10 R cycles (mailbox round trip + the row chain).
+            auto estimate = [&](const OswPass &ps) {
+                const double rate = (pd ? 17.5 : 23.0) * std::max(d0.n_sms, 1) * 1.125 * ps.R / (ps.R + 5.0);
+                const double t_pipe = 2.0 * ps.G * ps.R * cols / rate;
+                const double t_chain = longest * (230.0 + 10.0 * ps.R);
+                return std::max(t_pipe, t_chain) + 0.25 * std::min(t_pipe, t_chain);
+            };
+            double best = estimate(passes[0]);
+            int force_g = 0;
+            if (const char *e = getenv("OSW_MIN_G")) force_g = atoi(e);                 // experiments
+            std::vector<OswPass> alt(2);
+            for (int g = passes[0].G * 2; g <= 32; g *= 2) {
+                if (osw_plan_passes(q_len.data(), nq, alt.data(), 2, pd ? OSW_PLAN_PAIR_DB : OSW_PLAN_TWO_TRACK, g) != 1) continue;
+                const double t = estimate(alt[0]);
+                if (force_g ? g == force_g : t < best) { best = t; passes[0] = alt[0]; }
+            }
         }
+        passes.resize((size_t)n_pass);
     }
     const bool use_u16 = (c->kernel_mask & OSW_K_U16) != 0;
     uint64_t launches = 0, padded = 0, rescored = 0;
@@ -633,7 +637,7 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
     // ---- phase 1: first stage on every GPU ------------------------------------------------
     for (int i = 0; i < c->n_dev; ++i) {
         int rc = enqueue_search(c, c->devs[i], queries, q_off, nq, matrix, go, ge, (uint32_t)top_r,
-                                all_scores != nullptr, passes, wide, &slots[i], &launches, &padded);
+                                all_scores != nullptr, passes, &slots[i], &launches, &padded);
         if (rc != OSW_OK) return rc;
     }
     const double t_h2d = now_ms();
@@ -700,7 +704,7 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
         CK(cudaGetLastError());
         CK(cudaEventRecord(d.ev[2], d.st));
         const uint32_t r = (uint32_t)std::min<uint64_t>((uint64_t)top_r, N);
-        if (r) launches += osw_topr_select(d.d_scores, d.d_canon, N, nq, r, d.topr, d.st);
+        if (r) launches += osw_topr_select(d.d_scores, d.d_canon, N, std::max<uint64_t>(c->n_seqs_canon, 1), nq, r, d.topr, d.st);
         CK(cudaGetLastError());
         CK(cudaEventRecord(d.ev[3], d.st));
         if (r) CK(cudaMemcpyAsync(d.h_keys, d.topr.out_keys, (size_t)nq * r * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.st));

@@ -76,21 +76,22 @@ struct U16Params {
     uint64_t         bound_col0;
     int              gap_open_extend, gap_extend;
     uint32_t        *chunk_counter;
+    uint32_t         static_first;   // chunk groups dealt statically before the counter is used (set by the launcher)
     unsigned long long *cycle_acc;   // sum over CTAs of their elapsed clock64 cycles (one CTA per SM), or nullptr
 };
 int osw_launch_u16(const U16Params &p, const OswPass &pass, int n_sms, cudaStream_t st);
 
 // ---- device top-r (topr.cu) --------------------------------------------------------------
 struct TopRWork {            // per-device scratch, sized for nq_max queries
-    uint32_t *hist;          // [nq][256]
-    unsigned long long *prefix;   // [nq] key prefix found so far
-    uint32_t *remaining;     // [nq]
+    uint32_t *hist;          // [nq][8 rounds][256]
+    unsigned long long *prefix;   // [nq][8] key prefix after each round
+    uint32_t *remaining;     // [nq][8] rank still to find inside the prefix after each round
     uint32_t *out_count;     // [nq]
     unsigned long long *out_keys;  // [nq][r]
 };
 // Selects for each of nq rows the top_r largest keys (score<<32 | canonical index) into
 // w.out_keys (unordered).  Returns number of kernels launched.
-int osw_topr_select(const int32_t *scores, const uint32_t *canon, uint64_t n_seqs, int nq,
+int osw_topr_select(const int32_t *scores, const uint32_t *canon, uint64_t n_seqs, uint64_t n_canon, int nq,
                     uint32_t top_r, const TopRWork &w, cudaStream_t st);
 // Marks flagged scores: appends (q, seq) of every score == OSW_SCORE_FLAGGED to pairs.
 int osw_collect_flagged(const int32_t *scores, uint64_t n_seqs, int nq, uint2 *pairs,

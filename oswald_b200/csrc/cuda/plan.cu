@@ -15,7 +15,8 @@
 namespace {
 
 const int kG[4] = {4, 8, 16, 32};
-const int kR[8] = {16, 20, 24, 28, 32, 36, 40, 44};
+const int kNR = 10;
+const int kR[kNR] = {8, 12, 16, 20, 24, 28, 32, 36, 40, 44};
 int kRmax = 40;        // rows per lane of the full-height passes (OSW_RMAX overrides, for experiments)
 
 struct Track { std::vector<int> q; uint64_t rows = 0; };
@@ -95,7 +96,7 @@ extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int 
     {
         const int need_cap = std::max(lanes_needed(tr[0], q_len, 0, 0, r_cap), lanes_needed(tr[1], q_len, 0, 0, r_cap));
         const int n_min = (need_cap + 31) / 32;
-        for (int ri = 7; ri >= 0; --ri) {
+        for (int ri = kNR - 1; ri >= 0; --ri) {
             if (kR[ri] > r_cap) continue;
             const int need = std::max(lanes_needed(tr[0], q_len, 0, 0, kR[ri]), lanes_needed(tr[1], q_len, 0, 0, kR[ri]));
             if ((need + 31) / 32 <= n_min) r_full = kR[ri];
@@ -108,7 +109,7 @@ extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int 
         int G = 32, R = r_full;
         uint64_t best = ~0ull;
         for (int gi = 0; gi < 4; ++gi)
-            for (int ri = 0; ri < 8; ++ri) {
+            for (int ri = 0; ri < kNR; ++ri) {
                 if (kR[ri] > kRmax || (pair_db && kR[ri] > pd_rmax(kG[gi]))) continue;
                 const int need = std::max(lanes_needed(tr[0], q_len, cur[0], done[0], kR[ri]),
                                           lanes_needed(tr[1], q_len, cur[1], done[1], kR[ri]));

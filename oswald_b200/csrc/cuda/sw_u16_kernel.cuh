@@ -239,9 +239,17 @@ sw_u16_kernel(const KArgs a) {
     const uint32_t emit = ((fa & OSW_LANE_EMIT) && a.lane[0][t].q_len ? 1u : 0u) | ((fb & OSW_LANE_EMIT) && a.lane[1][t].q_len ? 2u : 0u);
     const uint32_t last_mask = emit ? OSW_COL_LAST : 0u;
 
+    // On a database of only a few chunks per warp the first chunks are dealt statically, warp w of
+    // CTA b taking group w * gridDim.x + b of the (descending) chunk list: every SM starts with the
+    // same mix of long and short chunks (measured + 2..6 % there, - 2.4 % on a large database, where
+    // the counter alone is used).  Later chunks come from the counter.
+    bool first_fetch = p.static_first != 0;
     for (;;) {
         // ---- fetch one chunk per group ---------------------------------------------------
-        if (lane == 0) s_chunk[wib] = atomicAdd(p.chunk_counter, (uint32_t)GROUPS);
+        if (lane == 0)
+            s_chunk[wib] = first_fetch ? (uint32_t)(wib * gridDim.x + blockIdx.x) * GROUPS
+                                       : p.static_first + atomicAdd(p.chunk_counter, (uint32_t)GROUPS);
+        first_fetch = false;
         __syncwarp();
         const uint32_t cbase = p.chunk_first + s_chunk[wib];
         __syncwarp();
@@ -454,8 +462,11 @@ int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
             return OSW_E_CUDA;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    profile_build_kernel<G, R, PD><<<32, 256, 0, st>>>(a);
-    sw_u16_kernel<G, R, THREADS, PD><<<n_sms, THREADS, smem, st>>>(a);
+    KArgs k = a;
+    const uint32_t slots = (uint32_t)n_sms * (THREADS / 32) * (32 / G);          // chunks in flight
+    k.p.static_first = a.p.chunk_end - a.p.chunk_first < 12 * slots ? slots : 0u;
+    profile_build_kernel<G, R, PD><<<32, 256, 0, st>>>(k);
+    sw_u16_kernel<G, R, THREADS, PD><<<n_sms, THREADS, smem, st>>>(k);
     return cudaGetLastError() == cudaSuccess ? OSW_OK : OSW_E_CUDA;
 }
 
@@ -473,6 +484,8 @@ int launch_one(const KArgs &a, int n_sms, cudaStream_t st) {
 template <int G>
 int launch_g(int R, const KArgs &a, int n_sms, cudaStream_t st) {
     switch (R) {
+        case 8: return launch_one<G, 8>(a, n_sms, st);
+        case 12: return launch_one<G, 12>(a, n_sms, st);
         case 16: return launch_one<G, 16>(a, n_sms, st);
         case 20: return launch_one<G, 20>(a, n_sms, st);
         case 24: return launch_one<G, 24>(a, n_sms, st);

@@ -3,10 +3,13 @@
 // The reference ranks every query's N scores with a full merge sort whose comparisons put,
 // among equal scores, the HIGHER canonical index first (utils.c:3-69; sort_scores :71-86).
 // That total order is the descending order of the 64-bit key (score << 32 | index), so the
-// top r hits are the r largest keys.  They are found by an MSB-first radix select (8 digits
-// of 8 bits): each round histograms the digit of the keys that still match the prefix, a
-// one-block kernel picks the digit that contains the r-th largest key, and a final pass
-// gathers the keys >= the r-th largest.  The host orders those r keys.
+// top r hits are the r largest keys.  They are found by an MSB-first radix select over the key's
+// bytes: round j histograms byte j of the keys that still match the prefix found so far, and the
+// NEXT kernel (the following round, or the final gather) starts by picking, from that histogram,
+// the digit that holds the r-th largest key.  Bytes that cannot be set are skipped: a score is
+// below 2^24 (at most 65535 columns x 31 per column, oswald_cuda.h), an index below the size of
+// the canonical database.  One kernel per round and one for the gather; the host orders the r
+// keys it gets.
 #include "osw_internal.h"
 
 namespace {
@@ -17,66 +20,77 @@ __device__ __forceinline__ unsigned long long make_key(int score, uint32_t canon
     return ((unsigned long long)(uint32_t)score << 32) | canon;    // scores are >= 0
 }
 
-// round `d` (0 = most significant byte): count digit values among keys whose higher bytes
-// equal prefix[q]'s.
+// Round j's pick, by a whole block of 256 threads: the digit whose bin holds the need-th largest
+// key among those matching the prefix.  Returns prefix | digit << shift and the rank left inside
+// that bin.  sh: 256 words of shared memory.
+__device__ __forceinline__ void pick_digit(const uint32_t *hist, int shift, unsigned long long pre, uint32_t need,
+                                           uint32_t *sh, unsigned long long *pre_out, uint32_t *need_out) {
+    __shared__ uint32_t s_digit, s_above;
+    const int v = threadIdx.x;
+    sh[v] = hist[v];
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {           // suffix sums: sh[v] = keys in bins >= v
+        const uint32_t add = v + o < 256 ? sh[v + o] : 0u;
+        __syncthreads();
+        sh[v] += add;
+        __syncthreads();
+    }
+    const uint32_t above = v < 255 ? sh[v + 1] : 0u;
+    if (sh[v] >= need && above < need) { s_digit = (uint32_t)v; s_above = above; }
+    __syncthreads();
+    *pre_out = pre | ((unsigned long long)s_digit << shift);
+    *need_out = need - s_above;
+    __syncthreads();
+}
+
+struct Rounds { int n; int shift[8]; };
+
+// State after round j is kept at slot j of prefix / remaining ([nq][8]); block x == 0 of a query
+// records it for the kernels that follow.
+__device__ __forceinline__ void state_before_round(const Rounds &rd, int j, int q, uint32_t r, const TopRWork &w, uint32_t *sh,
+                                                   unsigned long long *pre, uint32_t *need) {
+    if (j == 0) { *pre = 0; *need = r; return; }
+    unsigned long long p0 = 0; uint32_t n0 = r;
+    if (j >= 2) { p0 = w.prefix[q * 8 + j - 2]; n0 = w.remaining[q * 8 + j - 2]; }
+    pick_digit(w.hist + ((size_t)q * 8 + j - 1) * 256, rd.shift[j - 1], p0, n0, sh, pre, need);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { w.prefix[q * 8 + j - 1] = *pre; w.remaining[q * 8 + j - 1] = *need; }
+}
+
+// round j: count byte values among the keys whose higher (examined) bytes equal the prefix's
 __global__ void __launch_bounds__(THREADS)
-topr_hist_kernel(const int32_t *scores, const uint32_t *canon, uint64_t n, int d,
-                 const unsigned long long *prefix, uint32_t *hist) {
+topr_round_kernel(const int32_t *scores, const uint32_t *canon, uint64_t n, uint32_t r, int j, Rounds rd, TopRWork w) {
     __shared__ uint32_t sh[256];
     const int q = blockIdx.y;
+    unsigned long long pre; uint32_t need;
+    state_before_round(rd, j, q, r, w, sh, &pre, &need);
     sh[threadIdx.x] = 0;
     __syncthreads();
-    const int shift = 56 - 8 * d;
-    const unsigned long long pre = prefix[q];
-    const unsigned long long himask = d ? ~0ull << (shift + 8) : 0ull;
+    const int shift = rd.shift[j];
+    const unsigned long long himask = j ? ~0ull << (rd.shift[j - 1]) : 0ull;      // the bytes examined so far (skipped ones are 0 in every key)
     const int32_t *row = scores + (size_t)q * n;
     for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * THREADS) {
         unsigned long long k = make_key(row[i], canon[i]);
-        if ((k & himask) == (pre & himask)) atomicAdd(&sh[(k >> shift) & 255], 1u);
+        if ((k & himask) == pre) atomicAdd(&sh[(k >> shift) & 255], 1u);
     }
     __syncthreads();
-    if (sh[threadIdx.x]) atomicAdd(&hist[q * 256 + threadIdx.x], sh[threadIdx.x]);
+    if (sh[threadIdx.x]) atomicAdd(&w.hist[((size_t)q * 8 + j) * 256 + threadIdx.x], sh[threadIdx.x]);
 }
 
-// one block per query: choose the digit holding the `remaining`-th largest key.
-__global__ void topr_pick_kernel(int d, unsigned long long *prefix, uint32_t *remaining, uint32_t *hist) {
-    const int q = blockIdx.x;
-    if (threadIdx.x == 0) {
-        uint32_t need = remaining[q];
-        const int shift = 56 - 8 * d;
-        int digit = 0;
-        for (int v = 255; v >= 0; --v) {
-            uint32_t c = hist[q * 256 + v];
-            if (c >= need) { digit = v; break; }
-            need -= c;
-        }
-        prefix[q] |= (unsigned long long)digit << shift;
-        remaining[q] = need;
-    }
-    __syncthreads();
-    hist[q * 256 + threadIdx.x] = 0;          // ready for the next round (blockDim.x == 256)
-}
-
+// after the last round the prefix is the r-th largest key itself: gather the keys >= it
 __global__ void __launch_bounds__(THREADS)
-topr_gather_kernel(const int32_t *scores, const uint32_t *canon, uint64_t n, uint32_t top_r,
-                   const unsigned long long *threshold, uint32_t *out_count, unsigned long long *out_keys) {
+topr_gather_kernel(const int32_t *scores, const uint32_t *canon, uint64_t n, uint32_t r, Rounds rd, TopRWork w) {
+    __shared__ uint32_t sh[256];
     const int q = blockIdx.y;
-    const unsigned long long thr = threshold[q];
+    unsigned long long thr; uint32_t need;
+    state_before_round(rd, rd.n, q, r, w, sh, &thr, &need);
     const int32_t *row = scores + (size_t)q * n;
     for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * THREADS) {
         unsigned long long k = make_key(row[i], canon[i]);
         if (k >= thr) {
-            uint32_t slot = atomicAdd(&out_count[q], 1u);
-            if (slot < top_r) out_keys[(size_t)q * top_r + slot] = k;
+            uint32_t slot = atomicAdd(&w.out_count[q], 1u);
+            if (slot < r) w.out_keys[(size_t)q * r + slot] = k;
         }
     }
-}
-
-__global__ void topr_init_kernel(int nq, uint32_t r, unsigned long long *prefix, uint32_t *remaining,
-                                 uint32_t *out_count, uint32_t *hist) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nq) { prefix[i] = 0; remaining[i] = r; out_count[i] = 0; }
-    if (i < nq * 256) hist[i] = 0;
 }
 
 __global__ void __launch_bounds__(THREADS)
@@ -100,21 +114,23 @@ int grid_x(uint64_t n) {
 
 }  // namespace
 
-int osw_topr_select(const int32_t *scores, const uint32_t *canon, uint64_t n_seqs, int nq,
+int osw_topr_select(const int32_t *scores, const uint32_t *canon, uint64_t n_seqs, uint64_t n_canon, int nq,
                     uint32_t top_r, const TopRWork &w, cudaStream_t st) {
-    int launches = 0;
     uint32_t r = top_r < n_seqs ? top_r : (uint32_t)n_seqs;
-    topr_init_kernel<<<(nq * 256 + 255) / 256, 256, 0, st>>>(nq, r, w.prefix, w.remaining, w.out_count, w.hist);
-    ++launches;
-    if (r == 0) return launches;
-    dim3 grid(grid_x(n_seqs), nq);
-    for (int d = 0; d < 8; ++d) {
-        topr_hist_kernel<<<grid, THREADS, 0, st>>>(scores, canon, n_seqs, d, w.prefix, w.hist);
-        topr_pick_kernel<<<nq, 256, 0, st>>>(d, w.prefix, w.remaining, w.hist);
-        launches += 2;
+    if (r == 0) return 0;
+    Rounds rd;
+    rd.n = 0;
+    for (int byte = 6; byte >= 0; --byte) {          // byte 7 = score bits 24-31: never set
+        if (byte < 4 && byte > 0 && ((n_canon - 1) >> (8 * byte)) == 0) continue;     // index bytes above the database size
+        rd.shift[rd.n++] = 8 * byte;
     }
-    topr_gather_kernel<<<grid, THREADS, 0, st>>>(scores, canon, n_seqs, r, w.prefix, w.out_count, w.out_keys);
-    return launches + 1;
+    cudaMemsetAsync(w.hist, 0, (size_t)nq * 8 * 256 * sizeof(uint32_t), st);
+    cudaMemsetAsync(w.out_count, 0, (size_t)nq * sizeof(uint32_t), st);
+    dim3 grid(grid_x(n_seqs), nq);
+    for (int j = 0; j < rd.n; ++j)
+        topr_round_kernel<<<grid, THREADS, 0, st>>>(scores, canon, n_seqs, r, j, rd, w);
+    topr_gather_kernel<<<grid, THREADS, 0, st>>>(scores, canon, n_seqs, r, rd, w);
+    return rd.n + 1;
 }
 
 int osw_collect_flagged(const int32_t *scores, uint64_t n_seqs, int nq, uint2 *pairs,

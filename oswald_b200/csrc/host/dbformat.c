@@ -41,18 +41,7 @@ uint64_t osw_count_chunks(const uint64_t *offsets, uint64_t n_seqs, uint32_t chu
     return walk_chunks(offsets, n_seqs, chunk_cols, NULL, NULL);
 }
 
-/* columns of a chunk in the pair stream: sum over pairs of the longer length (ascending order:
- * the second sequence of a pair, or the single last one) */
-static uint64_t pair_columns(const uint64_t *off, uint64_t first, uint64_t ns) {
-    uint64_t cols = 0;
-    for (uint64_t k = 0; k < ns; k += 2) {
-        uint64_t i = first + (k + 1 < ns ? k + 1 : k);
-        cols += off[i + 1] - off[i];
-    }
-    return cols;
-}
-
-typedef struct { uint32_t shard, n_shards; uint64_t seqs, cols, bytes, chunks, pair_cols; uint32_t max_len;
+typedef struct { uint32_t shard, n_shards; uint64_t seqs, cols, bytes, chunks; uint32_t max_len;
                  const uint64_t *off; } tally_t;
 static void tally_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t cols) {
     tally_t *t = (tally_t *)u;
@@ -63,7 +52,7 @@ static void tally_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t 
 
 /* layout pass: directory entries in walk order (ascending length), offsets assigned in that order */
 typedef struct { uint32_t shard, n_shards; const uint64_t *off; osw_chunk *dir; uint64_t *first_seq;
-                 uint64_t n, seq_cursor, byte_cursor, pair_cursor, cols; uint32_t max_len; } layout_t;
+                 uint64_t n, seq_cursor, byte_cursor, cols; uint32_t max_len; } layout_t;
 static void layout_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t cols) {
     layout_t *l = (layout_t *)u;
     if (c % l->n_shards != l->shard) return;
@@ -71,9 +60,8 @@ static void layout_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t
     l->first_seq[l->n] = first;
     ck->stream_off = l->byte_cursor; ck->n_cols = (uint32_t)cols; ck->n_seqs = (uint32_t)ns;
     ck->seq0 = (uint32_t)l->seq_cursor; ck->canon0 = (uint32_t)first;
-    ck->pair_off = l->pair_cursor; ck->n_pair_cols = (uint32_t)pair_columns(l->off, first, ns); ck->reserved = 0;
+    ck->pair_off = 0; ck->n_pair_cols = 0; ck->reserved = 0;          /* (pair directory only) */
     l->byte_cursor += (cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
-    l->pair_cursor += ((uint64_t)ck->n_pair_cols + OSW_PAIR_ALIGN - 1) / OSW_PAIR_ALIGN * OSW_PAIR_ALIGN;
     l->seq_cursor += ns; l->cols += cols;
     uint64_t last = l->off[first + ns] - l->off[first + ns - 1];   /* longest: order is ascending */
     if (last > l->max_len) l->max_len = (uint32_t)last;
@@ -81,7 +69,7 @@ static void layout_cb(void *u, uint64_t c, uint64_t first, uint64_t ns, uint64_t
 }
 
 /* fills one chunk (both streams and the per-sequence tables); returns 1 if a residue code is invalid */
-static int fill_chunk(const uint8_t *res, const uint64_t *off, const osw_chunk *ck, uint64_t first, osw_shard *s, int with_pair) {
+static int fill_chunk(const uint8_t *res, const uint64_t *off, const osw_chunk *ck, uint64_t first, osw_shard *s) {
     int bad = 0;
     const uint64_t ns = ck->n_seqs;
     uint8_t *p = s->stream + ck->stream_off;
@@ -99,25 +87,46 @@ static int fill_chunk(const uint8_t *res, const uint64_t *off, const osw_chunk *
     }
     const uint64_t padded = ((uint64_t)ck->n_cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
     memset(p, OSW_COL_PADBYTE, padded - ck->n_cols);
-    if (!with_pair) return bad;
-    /* pair stream of the same chunk */
-    uint8_t *q = s->pair_stream + 2 * ck->pair_off;
-    for (uint64_t k = 0; k < ns; k += 2) {
-        const uint64_t ia = first + k, ib = first + k + 1;
-        const int has_b = k + 1 < ns;
-        const uint64_t la = off[ia + 1] - off[ia], lb = has_b ? off[ib + 1] - off[ib] : 0;
-        const uint64_t n = la > lb ? la : lb;
-        const uint8_t *a = res + off[ia], *b = has_b ? res + off[ib] : NULL;
-        for (uint64_t j = 0; j < n; ++j) {
-            q[2 * j] = (uint8_t)(j < la ? (a[j] & OSW_COL_CODE) : OSW_COL_PADBYTE);
-            q[2 * j + 1] = (uint8_t)(j < lb ? (b[j] & OSW_COL_CODE) : OSW_COL_PADBYTE);
-        }
-        if (n) { q[0] |= OSW_COL_FIRST; q[2 * (n - 1)] |= OSW_COL_LAST; }
-        q += 2 * n;
-    }
-    const uint64_t pc_padded = ((uint64_t)ck->n_pair_cols + OSW_PAIR_ALIGN - 1) / OSW_PAIR_ALIGN * OSW_PAIR_ALIGN;
-    memset(q, OSW_COL_PADBYTE, 2 * (pc_padded - ck->n_pair_cols));
     return bad;
+}
+
+/* The pair directory: the shard's sequences (local order = ascending length) taken two at a time,
+ * pairs grouped into chunks of about chunk_cols / 2 pair columns (the same work as a plain chunk;
+ * graded like the plain ones).  Its own walk rather than the plain chunks zipped, so that every
+ * pair chunk holds whole PAIRS whatever the plain chunk size is - with small chunks (small
+ * databases) most plain chunks hold a single sequence.  Pairs without columns (two empty
+ * sequences) get a chunk of their own, like empty sequences in the plain directory. */
+static int build_pair_directory(osw_shard *s, uint32_t chunk_cols) {
+    const uint64_t n_pairs = (s->n_seqs + 1) / 2;
+    osw_chunk *dir = (osw_chunk *)malloc((n_pairs ? n_pairs : 1) * sizeof(osw_chunk));
+    if (!dir) return -1;
+    const uint32_t coarse = chunk_cols / 2 ? chunk_cols / 2 : 1, fine = chunk_cols >= 1024 ? coarse / 4 : coarse;
+    const uint64_t fine_until = s->n_residues / 12;
+    uint64_t n = 0, cursor = 0, seen = 0;
+    uint64_t first = 0, cols = 0;          /* the open chunk: first sequence, pair columns so far */
+    for (uint64_t p = 0; p <= n_pairs; ++p) {
+        const uint64_t i = p < n_pairs ? 2 * p : s->n_seqs;
+        const uint64_t plen = p < n_pairs ? s->seq_len[i + 1 < s->n_seqs ? i + 1 : i] : 0;
+        const uint32_t target = seen < fine_until ? fine : coarse;
+        if (i > first && (p == n_pairs || cols + plen > target || (cols == 0 && plen > 0))) {
+            osw_chunk *ck = &dir[n++];
+            memset(ck, 0, sizeof *ck);
+            ck->n_seqs = (uint32_t)(i - first); ck->seq0 = (uint32_t)first; ck->canon0 = s->canon[first];
+            ck->pair_off = cursor; ck->n_pair_cols = (uint32_t)cols;
+            cursor += (cols + OSW_PAIR_ALIGN - 1) / OSW_PAIR_ALIGN * OSW_PAIR_ALIGN;
+            first = i; cols = 0;
+        }
+        if (p < n_pairs) {
+            cols += plen;
+            seen += s->seq_len[i] + (i + 1 < s->n_seqs ? s->seq_len[i + 1] : 0);
+        }
+    }
+    s->pair_chunks = (osw_chunk *)malloc((n ? n : 1) * sizeof(osw_chunk));
+    if (!s->pair_chunks) { free(dir); return -1; }
+    for (uint64_t k = 0; k < n; ++k) s->pair_chunks[n - 1 - k] = dir[k];       /* longest first */
+    s->n_pair_chunks = (uint32_t)n; s->pair_cols = cursor;
+    free(dir);
+    return 0;
 }
 
 int osw_shard_build_ex(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
@@ -136,20 +145,15 @@ int osw_shard_build_ex(const uint8_t *residues, const uint64_t *offsets, uint64_
     l.shard = shard; l.n_shards = n_shards; l.off = offsets; l.dir = dir; l.first_seq = first_seq;
     walk_chunks(offsets, n_seqs, chunk_cols, layout_cb, &l);
     out->n_seqs = l.seq_cursor; out->n_residues = l.cols; out->stream_bytes = l.byte_cursor;
-    out->pair_cols = l.pair_cursor; out->n_chunks = (uint32_t)l.n; out->max_len = l.max_len;
+    out->n_chunks = (uint32_t)l.n; out->max_len = l.max_len;
     out->external_streams = alloc != NULL;
-    if (alloc) {
-        out->stream = (uint8_t *)alloc(out->stream_bytes ? out->stream_bytes : 1, alloc_user);
-        if (with_pair) out->pair_stream = (uint8_t *)alloc(out->pair_cols ? 2 * out->pair_cols : 1, alloc_user);
-    } else {
-        out->stream = (uint8_t *)malloc(out->stream_bytes ? out->stream_bytes : 1);
-        if (with_pair) out->pair_stream = (uint8_t *)malloc(out->pair_cols ? 2 * out->pair_cols : 1);
-    }
+    if (alloc) out->stream = (uint8_t *)alloc(out->stream_bytes ? out->stream_bytes : 1, alloc_user);
+    else out->stream = (uint8_t *)malloc(out->stream_bytes ? out->stream_bytes : 1);
     out->chunks  = (osw_chunk *)malloc((l.n ? l.n : 1) * sizeof(osw_chunk));
     out->canon   = (uint32_t *)malloc((out->n_seqs ? out->n_seqs : 1) * sizeof(uint32_t));
     out->seq_off = (uint64_t *)malloc((out->n_seqs ? out->n_seqs : 1) * sizeof(uint64_t));
     out->seq_len = (uint32_t *)malloc((out->n_seqs ? out->n_seqs : 1) * sizeof(uint32_t));
-    if (!out->stream || (with_pair && !out->pair_stream) || !out->chunks || !out->canon || !out->seq_off || !out->seq_len) {
+    if (!out->stream || !out->chunks || !out->canon || !out->seq_off || !out->seq_len) {
         free(dir); free(first_seq);
         osw_shard_free(out);
         return -1;
@@ -157,11 +161,18 @@ int osw_shard_build_ex(const uint8_t *residues, const uint64_t *offsets, uint64_
     int bad = 0;
     const long long n_chunks = (long long)l.n;
 #pragma omp parallel for schedule(dynamic, 64) reduction(| : bad)
-    for (long long k = 0; k < n_chunks; ++k) bad |= fill_chunk(residues, offsets, &dir[k], first_seq[k], out, with_pair);
+    for (long long k = 0; k < n_chunks; ++k) bad |= fill_chunk(residues, offsets, &dir[k], first_seq[k], out);
     /* the directory is stored in reverse so that index 0 is the longest-sequence chunk */
     for (uint64_t k = 0; k < l.n; ++k) out->chunks[l.n - 1 - k] = dir[k];
     free(dir); free(first_seq);
     if (bad) { osw_shard_free(out); return -2; }
+    if (build_pair_directory(out, chunk_cols) != 0) { osw_shard_free(out); return -1; }
+    if (with_pair) {
+        const size_t bytes = out->pair_cols ? 2 * out->pair_cols : 1;
+        out->pair_stream = (uint8_t *)(alloc ? alloc(bytes, alloc_user) : malloc(bytes));
+        if (!out->pair_stream) { osw_shard_free(out); return -1; }
+        osw_shard_fill_pair(out, out->stream, out->pair_stream);
+    }
     return 0;
 }
 
@@ -170,13 +181,14 @@ int osw_shard_build(const uint8_t *residues, const uint64_t *offsets, uint64_t n
     return osw_shard_build_ex(residues, offsets, n_seqs, shard, n_shards, chunk_cols, 1, NULL, NULL, out);
 }
 
-/* Pair stream from the plain one (same residues, flags stripped): used when the pair stream is
- * first needed after the caller's database arrays are gone. */
+/* Pair stream from the plain one (same residues, flags stripped): sequences 2p and 2p+1 of a pair
+ * chunk zipped column by column.  Also used when the pair stream is first needed after the
+ * caller's database arrays are gone. */
 void osw_shard_fill_pair(const osw_shard *s, const uint8_t *stream, uint8_t *pair) {
-    const long long n_chunks = (long long)s->n_chunks;
+    const long long n_chunks = (long long)s->n_pair_chunks;
 #pragma omp parallel for schedule(dynamic, 64)
     for (long long c = 0; c < n_chunks; ++c) {
-        const osw_chunk *ck = &s->chunks[c];
+        const osw_chunk *ck = &s->pair_chunks[c];
         uint8_t *q = pair + 2 * ck->pair_off;
         for (uint32_t k = 0; k < ck->n_seqs; k += 2) {
             const uint64_t la = s->seq_len[ck->seq0 + k];
@@ -200,6 +212,6 @@ void osw_shard_fill_pair(const osw_shard *s, const uint8_t *stream, uint8_t *pai
 void osw_shard_free(osw_shard *s) {
     if (!s) return;
     if (!s->external_streams) { free(s->stream); free(s->pair_stream); }   /* external ones belong to the allocator's owner */
-    free(s->chunks); free(s->canon); free(s->seq_off); free(s->seq_len);
+    free(s->chunks); free(s->pair_chunks); free(s->canon); free(s->seq_off); free(s->seq_len);
     memset(s, 0, sizeof *s);
 }

@@ -16,14 +16,16 @@
  * Chunk streams start on 128-byte boundaries (padding bytes are OSW_COL_PADBYTE), so a warp reads a
  * stream with coalesced 128-bit loads.
  *
- * Every chunk also exists as a PAIR STREAM for searches with a single query (or very unequal
+ * The shard also exists as a PAIR STREAM for searches with a single query (or very unequal
  * query sets), where the two 16-bit halves of the kernel's words score two DIFFERENT database
- * sequences against the same query rows: sequences 2p and 2p+1 of the chunk (neighbours in
+ * sequences against the same query rows: the shard's sequences 2p and 2p+1 (neighbours in
  * length) are zipped column by column, the shorter one padded with OSW_COL_PADBYTE (which scores
  * 0 against everything and so cannot raise a maximum).  Two bytes per column:
  *      byte 0   residue of the first sequence | FIRST / LAST flags of the pair's columns
- *      byte 1   residue of the second sequence (padding if the chunk has an odd sequence count)
- * Pair chunks start on 64-column (128-byte) boundaries.  Chunk c of the database is dealt to shard
+ *      byte 1   residue of the second sequence (padding for the single last sequence)
+ * The pairs are grouped into PAIR CHUNKS with a directory of their own (about chunk_cols / 2 pair
+ * columns each: the same work as a plain chunk); pair chunks start on 64-column (128-byte)
+ * boundaries.  Chunk c of the database is dealt to shard
  * (c mod n_shards): every shard gets the same mix of lengths and the same number of
  * residues to within one chunk - the residue-balanced split across GPUs.
  */
@@ -48,8 +50,8 @@ typedef struct osw_chunk {
     uint32_t n_seqs;       /* whole sequences in the chunk */
     uint32_t seq0;         /* shard-local index of its first sequence */
     uint32_t canon0;       /* canonical index of its first sequence (the rest follow) */
-    uint64_t pair_off;     /* column offset of the chunk in the shard's PAIR stream (2 bytes per column) */
-    uint32_t n_pair_cols;  /* columns of the chunk in the pair stream */
+    uint64_t pair_off;     /* pair directory: column offset of the chunk in the PAIR stream (2 bytes per column) */
+    uint32_t n_pair_cols;  /* pair directory: columns of the chunk in the pair stream */
     uint32_t reserved;
 } osw_chunk;
 
@@ -64,6 +66,8 @@ typedef struct osw_shard {
     uint64_t   pair_cols;      /* columns of the pair stream (multiple of 64) */
     uint8_t   *pair_stream;    /* 2 * pair_cols bytes */
     osw_chunk *chunks;         /* in DESCENDING length order (longest work is handed out first) */
+    osw_chunk *pair_chunks;    /* the pair directory (same order; stream_off / n_cols unused) */
+    uint32_t   n_pair_chunks;
     uint32_t  *canon;          /* canon[local] = canonical index */
     uint64_t  *seq_off;        /* seq_off[local] = stream offset of the sequence's first column */
     uint32_t  *seq_len;        /* seq_len[local] */

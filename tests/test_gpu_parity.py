@@ -346,7 +346,7 @@ def test_query_batches(built, monkeypatch):
     with ob.Searcher(1) as s:
         s.load_db(db)
         tm = check(s, db, q, "blosum62", 10, 2, 10)
-        assert tm["launches"] >= 4 * 20            # four batches, each with its own scoring + top-r launches
+        assert tm["launches"] >= 4 * 8            # four batches, each with its own scoring + top-r launches
 
 
 def test_streamed_database_windows(built):

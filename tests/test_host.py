@@ -47,7 +47,8 @@ class Shard(C.Structure):
                 ("n_chunks", C.c_uint32), ("max_len", C.c_uint32), ("external_streams", C.c_int),
                 ("stream", C.POINTER(C.c_uint8)),
                 ("pair_cols", C.c_uint64), ("pair_stream", C.POINTER(C.c_uint8)),
-                ("chunks", C.POINTER(Chunk)), ("canon", C.POINTER(C.c_uint32)),
+                ("chunks", C.POINTER(Chunk)), ("pair_chunks", C.POINTER(Chunk)), ("n_pair_chunks", C.c_uint32),
+                ("canon", C.POINTER(C.c_uint32)),
                 ("seq_off", C.POINTER(C.c_uint64)), ("seq_len", C.POINTER(C.c_uint32))]
 
 
@@ -109,8 +110,19 @@ def test_chunk_streams(built, n_shards):
             assert pos - ck.stream_off == ck.n_cols
             pad_end = ck.stream_off + (ck.n_cols + 127) // 128 * 128
             assert np.all(stream[pos:pad_end] == 23)
-            # the pair stream of the chunk: sequences 2p, 2p+1 zipped, two bytes per column
-            seqs = [db.sequence(ck.canon0 + k) for k in range(ck.n_seqs)]
+        # the pair directory: the shard's sequences 2p, 2p+1 zipped (two bytes per column), whole
+        # pairs per chunk, every sequence in exactly one pair chunk, longest chunks first
+        nxt = s.n_seqs
+        for c in range(s.n_pair_chunks):
+            ck = s.pair_chunks[c]
+            assert ck.seq0 + ck.n_seqs == nxt and ck.n_seqs > 0
+            nxt = ck.seq0
+            assert ck.seq0 % 2 == 0 and (ck.n_seqs % 2 == 0 or ck.seq0 + ck.n_seqs == s.n_seqs)
+            seqs = [db.sequence(s.canon[ck.seq0 + k]) for k in range(ck.n_seqs)]
+            if ck.n_pair_cols == 0:
+                assert all(len(x) == 0 for x in seqs)          # column-less pairs never share a chunk with real ones
+            else:
+                assert all(max(len(seqs[k]), len(seqs[min(k + 1, len(seqs) - 1)])) > 0 for k in range(0, len(seqs), 2))
             sa, sb, n_pairs = emu_u16.build_pair_streams(seqs)
             assert ck.pair_off % 64 == 0 and ck.n_pair_cols == len(sa)
             got = pair[2 * ck.pair_off:2 * (ck.pair_off + ck.n_pair_cols)].reshape(-1, 2)
@@ -118,6 +130,7 @@ def test_chunk_streams(built, n_shards):
             assert np.array_equal(got[:, 1], np.array(sb, dtype=np.uint8) & 31)
             pad_cols = (ck.n_pair_cols + 63) // 64 * 64
             assert np.all(pair[2 * (ck.pair_off + ck.n_pair_cols):2 * (ck.pair_off + pad_cols)] == 23)
+        assert nxt == 0
         built.osw_shard_free(C.byref(s))
     assert np.all(seen == 1)                           # every sequence in exactly one shard
     if n_shards > 1:
@@ -221,7 +234,7 @@ def test_pass_planner_layout(built):
         covered = {q: 0 for q in range(len(lens))}
         track_of = {}
         for pi, p in enumerate(passes):
-            assert p.G in (4, 8, 16, 32) and p.R in (16, 20, 24, 28, 32, 36, 40, 44)
+            assert p.G in (4, 8, 16, 32) and p.R in (8, 12, 16, 20, 24, 28, 32, 36, 40, 44)
             assert pi == 0 or p.G == 32
             for half in (0, 1):
                 for t in range(p.G):
