@@ -323,11 +323,19 @@ def main():
                     "frac_of_kernel_issue_bound": (achieved_gcups / (2.0 * r_dpx / 4.5 * n_sms * sm_mhz * 1e-3)) if achieved_gcups else None,
                     "sm_mhz": sm_mhz, "padded_over_useful_cells": tm["padded_cells"] / max(local_cells, 1),
                     "calibration": cal, "peak_source": "calibrated on this GPU in this run (osw_calibrate)",
-                    "hbm": {"achieved_GBps": tm["db_stream_bytes"] / (score_ms / 1e3) / 1e9 if score_ms else None,
+                    "hbm": {"achieved_GBps": (tm["db_stream_bytes"] + tm["bound_bytes"]) / (score_ms / 1e3) / 1e9 if score_ms else None,
                             "peak_GBps": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
                             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
-                            "algorithmic_bytes_per_cell": tm["db_stream_bytes"] / max(local_cells, 1)},
+                            "algorithmic_bytes_per_cell": (tm["db_stream_bytes"] + tm["bound_bytes"]) / max(local_cells, 1),
+                            "algorithmic_bytes_per_launch": (tm["db_stream_bytes"] + tm["bound_bytes"]) / max(tm["score_launches"], 1),
+                            "what": "column stream (1 B per column per pass) + bottom rows handed between passes (8 B per column each way)"},
                     "traffic": None}
+        # measured DRAM bytes per first-stage launch of this workload (ncu, tools/gpu_profile.sh), when on file
+        tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tr_path) and args.seqs_per_gpu == SEQS_PER_GPU and not args.query_lengths:
+            tr = json.load(open(tr_path))
+            roofline["traffic"] = tr["dram_bytes_per_launch"]
+            roofline["traffic_source"] = tr["source"]
         out = {"metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u16x2 (packed 16-bit DPX) + int32 re-score", "data": "synthetic",

@@ -72,6 +72,8 @@ typedef struct osw_timing {
     uint64_t launches;         /* kernels launched by this call (all GPUs) */
     uint64_t sm_cycles;        /* busy SM-cycles of the first-stage kernels summed over the SMs of GPU 0 (clock64) */
     uint64_t db_stream_bytes;  /* database bytes read by the first-stage kernels (algorithmic) */
+    uint64_t bound_bytes;      /* bottom-row bytes they read and wrote between passes (algorithmic: 8 per column each way) */
+    uint64_t score_launches;   /* first-stage scoring launches (all GPUs) */
 } osw_timing;
 
 /* ---- device discovery: replaces display_device_info(), reference utils.c:175-253 -------- */

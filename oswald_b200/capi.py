@@ -23,7 +23,8 @@ class OswTiming(C.Structure):
     _fields_ = [("device_ms", C.c_double), ("score_ms", C.c_double), ("rescore_ms", C.c_double),
                 ("topr_ms", C.c_double), ("h2d_ms", C.c_double), ("wall_ms", C.c_double),
                 ("cells", C.c_uint64), ("padded_cells", C.c_uint64), ("rescored_pairs", C.c_uint64),
-                ("launches", C.c_uint64), ("sm_cycles", C.c_uint64), ("db_stream_bytes", C.c_uint64)]
+                ("launches", C.c_uint64), ("sm_cycles", C.c_uint64), ("db_stream_bytes", C.c_uint64),
+                ("bound_bytes", C.c_uint64), ("score_launches", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -578,7 +578,7 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
         total.device_ms += tm.device_ms; total.score_ms += tm.score_ms; total.rescore_ms += tm.rescore_ms; total.topr_ms += tm.topr_ms;
         total.h2d_ms += tm.h2d_ms; total.wall_ms += tm.wall_ms; total.cells += tm.cells; total.padded_cells += tm.padded_cells;
         total.rescored_pairs += tm.rescored_pairs; total.launches += tm.launches; total.sm_cycles += tm.sm_cycles;
-        total.db_stream_bytes += tm.db_stream_bytes;
+        total.db_stream_bytes += tm.db_stream_bytes; total.bound_bytes += tm.bound_bytes; total.score_launches += tm.score_launches;
     }
     if (timing) *timing = total;
     return OSW_OK;
@@ -775,7 +775,11 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
     tm.launches = launches;
     tm.db_stream_bytes = 0;
     for (int i = 0; i < c->n_dev; ++i)
-        for (const LaunchRecord &lr : c->devs[i].trace) tm.db_stream_bytes += (lr.pair_db ? 2 : 1) * lr.cols;
+        for (const LaunchRecord &lr : c->devs[i].trace) {
+            tm.db_stream_bytes += (lr.pair_db ? 2 : 1) * lr.cols;
+            tm.bound_bytes += 8 * lr.cols * (uint64_t)((lr.has_in ? 1 : 0) + (lr.has_out ? 1 : 0));
+            ++tm.score_launches;
+        }
     if (timing) *timing = tm;
     return OSW_OK;
 }

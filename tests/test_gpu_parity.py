@@ -372,3 +372,19 @@ def test_streamed_database_windows(built):
         s.set_kernels(capi.OSW_K_I32)
         with pytest.raises(capi.OswError):
             s.search(q, ob.matrix("pam30"), 9, 1, top=5)
+
+
+@pytest.mark.parametrize("min_g", ["4", "8", "16", "32"])
+def test_forced_group_widths(built, monkeypatch, min_g):
+    """Single-pass plans: every group width the small-database estimate can pick (G = 4 ... 32, down
+    to 8 rows per lane) gives the same scores; a tiny database deals its first chunks statically."""
+    monkeypatch.setenv("OSW_MIN_G", min_g)
+    rng = np.random.default_rng(31 + int(min_g))
+    seqs = rand_seqs(rng, 1200, 0, 500) + [AA[rng.integers(0, 20, size=n)] for n in (2500, 9000)]
+    db = make_db(seqs)
+    with ob.Searcher(1) as s:
+        s.load_db(db)
+        for lens in ([144], [30], [90, 100], [33, 150, 7, 61]):
+            q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in lens])
+            for mode in MODES.values():
+                check(s, db, q, "blosum62", 10, 2, 10, mask=mode)

@@ -1,6 +1,7 @@
 #!/bin/bash
-# ncu evidence for the current build (one GPU): launch list + one full capture of the top kernel.
-# usage (under gpurun): bash tools/gpu_profile.sh <tag>
+# ncu evidence for the current build (one GPU): launch list + one full capture of the top kernel
+# (on a 30 000-sequence slice: ~40 replays per kernel) + DRAM bytes of the 17 first-stage launches of
+# one full-size search.   usage (under gpurun): bash tools/gpu_profile.sh <tag>
 TAG=${1:-prof}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 0 --seqs-per-gpu 30000 --no-cpu-baseline"
@@ -10,4 +11,10 @@ echo "launch list rc=$?"
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:sw_u16 -s 14 -c 2 -f -o gpurun_out/${TAG} $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "full capture rc=$?"
+FULL="python bench.py --steps 1 --warmup 0 --no-cpu-baseline"
+$FULL > gpurun_out/${TAG}_plain3.log 2>&1 &&
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:sw_u16_kernel -c 17 --csv \
+    --log-file gpurun_out/${TAG}_traffic.csv $FULL > gpurun_out/${TAG}_ncu3.log 2>&1
+echo "traffic capture rc=$?"
+python tools/ncu_traffic.py gpurun_out/${TAG}_traffic.csv gpurun_out/${TAG}_traffic.json "$FULL"
 ls -la gpurun_out/
