@@ -12,6 +12,9 @@ $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:sw_u16 -s 14 -c 2 -f -o gpurun_out/${TAG} $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "full capture rc=$?"
 FULL="python bench.py --steps 1 --warmup 0 --no-cpu-baseline"
+$FULL > gpurun_out/${TAG}_plain4.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_full.csv $FULL > gpurun_out/${TAG}_ncu4.log 2>&1
+echo "full-size launch list rc=$?"
 $FULL > gpurun_out/${TAG}_plain3.log 2>&1 &&
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:sw_u16_kernel -c 17 --csv \
     --log-file gpurun_out/${TAG}_traffic.csv $FULL > gpurun_out/${TAG}_ncu3.log 2>&1
