@@ -137,6 +137,36 @@ def test_chunk_streams(built, n_shards):
         assert max(residues) - min(residues) <= 2 * 1024 + int(lens.max())     # residue-balanced
 
 
+@pytest.mark.parametrize("lens", [[5], [0], [0, 0, 0], [0, 7], [3, 3], [1, 2, 3], [0, 0, 0, 4, 9], [600, 700, 5000],
+                                  [10] * 7 + [65535, 65535]])
+def test_pair_directory_edge_cases(built, lens):
+    """Whole pairs per pair chunk, whatever the plain chunk size: single / odd / empty sequences."""
+    rng = np.random.default_rng(3)
+    lens = np.array(sorted(lens), dtype=np.uint64)
+    db = ob.Database.from_lengths(lens, AA[rng.integers(0, 20, size=int(lens.sum()))])
+    for chunk_cols in (64, 256, 8192):
+        s = build_shard(built, db, 0, 1, chunk_cols)
+        pair = np.ctypeslib.as_array(s.pair_stream, shape=(max(2 * s.pair_cols, 1),))
+        covered = 0
+        for c in range(s.n_pair_chunks):
+            ck = s.pair_chunks[c]
+            assert ck.seq0 % 2 == 0 and ck.n_seqs > 0
+            covered += ck.n_seqs
+            seqs = [db.sequence(s.canon[ck.seq0 + k]) for k in range(ck.n_seqs)]
+            sa, sb, n_pairs = emu_u16.build_pair_streams(seqs)
+            assert ck.n_pair_cols == len(sa)
+            if ck.n_pair_cols:
+                got = pair[2 * ck.pair_off:2 * (ck.pair_off + ck.n_pair_cols)].reshape(-1, 2)
+                assert np.array_equal(got[:, 0], np.array(sa, dtype=np.uint8))
+                assert np.array_equal(got[:, 1], np.array(sb, dtype=np.uint8) & 31)
+                # the kernel counts pairs by their LAST columns: one per pair of the chunk
+                assert int(((got[:, 0] >> 6) & 1).sum()) == (ck.n_seqs + 1) // 2
+            else:
+                assert all(len(x) == 0 for x in seqs)
+        assert covered == db.n_seqs
+        built.osw_shard_free(C.byref(s))
+
+
 def test_host_mirror_matches_reference_preprocessing():
     meta = load_case("g3_kat")
     db = ob.preprocess_db(meta["db_fasta"])
