@@ -561,16 +561,25 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
     for (int k = 0; k < 24 * 32; ++k)
         if (matrix[k] < -32 || matrix[k] > 31) { snprintf(g_err, sizeof g_err, "substitution score %d is outside -32..31", matrix[k]); return OSW_E_ARG; }
     // The score matrix (4 bytes per query and sequence) is the largest per-search buffer: many
-    // queries go through in batches that keep it under 8 GiB per GPU (OSW_SCORE_BUDGET_KB overrides).
+    // queries go through in batches that keep it under 8 GiB per GPU (OSW_SCORE_BUDGET_KB
+    // overrides).  A batch also stays within what one plan can hold: 16 384 queries (grid limit of
+    // the per-query kernels) and a million query rows (a few hundred passes, far below MAX_PASSES
+    // and, times the segments of a streamed database, MAX_LAUNCH_SLOTS).
     uint64_t n_max = 1;
     for (int i = 0; i < c->n_dev; ++i) n_max = std::max<uint64_t>(n_max, c->devs[i].shard.n_seqs);
     uint64_t budget = (uint64_t)8 << 30;
     if (const char *e = getenv("OSW_SCORE_BUDGET_KB")) { const long long v = atoll(e); if (v >= 1) budget = (uint64_t)v << 10; }
-    const int batch = (int)std::max<uint64_t>(2, std::min<uint64_t>((uint64_t)nq, budget / (4 * n_max)));
+    const int batch = (int)std::max<uint64_t>(2, std::min<uint64_t>(std::min<uint64_t>((uint64_t)nq, 16384), budget / (4 * n_max)));
+    const uint64_t max_rows = 1u << 20;
     osw_timing total;
     memset(&total, 0, sizeof total);
-    for (int q0 = 0; q0 < nq; q0 += batch) {
-        const int nb = std::min(batch, nq - q0);
+    for (int q0 = 0, nb = 0; q0 < nq; q0 += nb) {
+        nb = 0;
+        uint64_t rows = 0;
+        while (q0 + nb < nq && nb < batch && (nb == 0 || rows + (q_off[q0 + nb + 1] - q_off[q0 + nb]) <= max_rows)) {
+            rows += q_off[q0 + nb + 1] - q_off[q0 + nb];
+            ++nb;
+        }
         osw_timing tm;
         int rc = search_batch(c, queries, q_off + q0, nb, matrix, go, ge, top_r, hits ? hits + (size_t)q0 * top_r : nullptr,
                               n_hits ? n_hits + q0 : nullptr, all_scores ? all_scores + (size_t)q0 * c->n_seqs_canon : nullptr, &tm);

@@ -388,3 +388,15 @@ def test_forced_group_widths(built, monkeypatch, min_g):
             q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in lens])
             for mode in MODES.values():
                 check(s, db, q, "blosum62", 10, 2, 10, mask=mode)
+
+
+def test_many_tiny_queries(built):
+    """20 000 queries of 1..6 residues: more than one batch (16 384 queries per plan), hundreds of
+    passes of one-query lanes; every score and hit list still equals the oracle's."""
+    rng = np.random.default_rng(2024)
+    db = make_db(rand_seqs(rng, 60, 0, 40))
+    q = ob.Queries.from_list([AA[rng.integers(0, 20, size=int(m))] for m in rng.integers(1, 7, size=20000)])
+    with ob.Searcher(1) as s:
+        s.load_db(db)
+        tm = check(s, db, q, "blosum62", 10, 2, 3)
+        assert tm["score_launches"] >= 2
