@@ -27,7 +27,7 @@ namespace {
 constexpr uint32_t MAX_LAUNCH_SLOTS = 4096;
 constexpr uint32_t FLAG_CAPACITY_MIN = 1u << 16;
 
-struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; };
+struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; uint32_t express; };
 
 struct DevState {
     int dev = -1, n_sms = 0;
@@ -381,6 +381,24 @@ namespace {
 
 constexpr int MAX_PASSES = 2048;
 
+// Timing model of one first-stage launch, in SM cycles (measured on B200: tools/dpx_latency.cu, the
+// OSW_TRACE reports of bench.py on small databases; profiles/r1_ncu_summary.md).  A warp-step (one
+// column for each of the warp's 32/G groups) takes `issue` cycles of its scheduler's issue slots /
+// DPX pipe, and at least `alone` cycles from start to end (mailbox and profile reads, then the
+// dependent row chain: 14 cycles per row, two row segments in parallel).
+struct LaunchModel {
+    double issue, alone, contended, t_pipe;
+    int groups, warps_per_scheduler;
+    LaunchModel(int G, int R, bool pd, double cols, int n_sms) {
+        groups = 32 / G;
+        warps_per_scheduler = R > 32 ? 3 : 4;                       // 384- / 512-thread CTAs
+        issue = (pd ? 11.7 : 9.0) * R + 45.0;
+        alone = 140.0 + 7.0 * R;
+        contended = std::max(alone, warps_per_scheduler * issue);
+        t_pipe = cols / ((double)groups * std::max(n_sms, 1) * 4.0) * issue;
+    }
+};
+
 int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32_t *q_off, int nq,
                    const int8_t *matrix, int go, int ge, uint32_t top_r, bool want_all,
                    const std::vector<OswPass> &passes,
@@ -473,6 +491,25 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             up.stream = win_ptr ? win_ptr : d.d_stream; up.pair_stream = win_ptr ? win_ptr : d.d_pair; up.stream_col0 = win_col0;
             up.chunks = pd ? d.d_pair_chunks : d.d_chunks;
             up.chunk_first = first; up.chunk_end = end; up.static_first = 0;
+            uint64_t cols = 0;
+            if (first == 0 && end == n_dir) cols = pd ? s.pair_cols : s.n_residues;
+            else for (uint32_t k = first; k < end; ++k) cols += chunk_cols(k);
+            // When walking the longest chunk among three other busy warps would take clearly longer
+            // than the whole launch needs for its cell updates, the longest chunks get express CTAs:
+            // one warp per scheduler, so that they advance at the latency of a step rather than at a
+            // quarter of the scheduler's issue rate.  (Threshold 1.5 measured: at a ratio of 1.15 the
+            // express CTAs cost 4 %, at 1.9 they gain 6 %, at 3.5 and above 20-40 %.)
+            up.express_ctas = 0;
+            if (end > first && !getenv("OSW_NO_EXPRESS")) {
+                const LaunchModel m(ps.G, ps.R, pd, (double)cols, d.n_sms);
+                const double longest = (double)chunk_cols(first);
+                if (longest * m.contended > 1.5 * m.t_pipe) {
+                    const double cut = longest * m.alone / m.contended;      // shorter chunks finish in time anyway
+                    uint32_t n = 0;
+                    while (first + n < end && n < 64u * m.groups && (double)chunk_cols(first + n) > cut) ++n;
+                    up.express_ctas = std::min<uint32_t>(16, std::max<uint32_t>(1, (n + 4 * m.groups - 1) / (4 * m.groups)));
+                }
+            }
             up.queries = d.d_queries; up.q_off = d.d_qoff; up.matrix = d.d_matrix;
             up.profile = d.d_profile;
             up.scores = d.d_scores; up.n_seqs = N;
@@ -482,10 +519,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             up.cycle_acc = d.d_cycles + slot;
             int rc2 = osw_launch_u16(up, ps, d.n_sms, d.st);
             if (rc2 != OSW_OK) { cuda_fail(cudaGetLastError(), "sw_u16 launch", __LINE__); return rc2; }
-            uint64_t cols = 0;
-            if (first == 0 && end == n_dir) cols = pd ? s.pair_cols : s.n_residues;
-            else for (uint32_t k = first; k < end; ++k) cols += chunk_cols(k);
-            d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols});
+            d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols, up.express_ctas});
             ++slot; *launches += 2;               // profile_build_kernel + sw_u16_kernel
             *padded_cells += (uint64_t)ps.G * ps.R * 2 * cols;
             return OSW_OK;
@@ -617,15 +651,10 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
             const bool pd = passes[0].pair_db != 0;
             const double cols = (double)(pd ? s0.pair_cols : s0.n_residues);
             const double longest = !(pd ? s0.n_pair_chunks : s0.n_chunks) ? 0.0 : (double)(pd ? s0.pair_chunks[0].n_pair_cols : s0.chunks[0].n_cols);
-            // Measured on B200 (profiles/r1_ncu_summary.md, "small databases"): all SMs busy, a pass
-            // sustains 23 padded cell updates per SM-cycle (17.5 in pair-database mode) at R = 40, less
-            // with few rows per lane (about 5 rows' worth of per-step bookkeeping); a step of the
-            // longest chunk's warp takes about 230 + 10 R cycles (mailbox round trip + the row chain).
             auto estimate = [&](const OswPass &ps) {
-                const double rate = (pd ? 17.5 : 23.0) * std::max(d0.n_sms, 1) * 1.125 * ps.R / (ps.R + 5.0);
-                const double t_pipe = 2.0 * ps.G * ps.R * cols / rate;
-                const double t_chain = longest * (230.0 + 10.0 * ps.R);
-                return std::max(t_pipe, t_chain) + 0.25 * std::min(t_pipe, t_chain);
+                const LaunchModel m(ps.G, ps.R, pd, cols, d0.n_sms);
+                const double t_chain = longest * m.alone;               // (the longest chunks get express CTAs)
+                return std::max(m.t_pipe, t_chain) + 0.25 * std::min(m.t_pipe, t_chain);
             };
             double best = estimate(passes[0]);
             int force_g = 0;
@@ -744,8 +773,8 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
             for (uint32_t k = 0; k < slots[i] && k < d.trace.size(); ++k) {
                 const LaunchRecord &lr = d.trace[k];
                 const double cells = 2.0 * lr.G * lr.R * (double)lr.cols;
-                fprintf(stderr, "osw trace: launch %u/%zu G=%d R=%d in=%d out=%d pairdb=%d chunks [%u,%u)  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
-                        k + 1, d.trace.size(), lr.G, lr.R, lr.has_in, lr.has_out, lr.pair_db, lr.first, lr.end,
+                fprintf(stderr, "osw trace: launch %u/%zu G=%d R=%d in=%d out=%d pairdb=%d express=%u chunks [%u,%u)  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
+                        k + 1, d.trace.size(), lr.G, lr.R, lr.has_in, lr.has_out, lr.pair_db, lr.express, lr.first, lr.end,
                         (unsigned long long)(d.h_cycles[k] / d.n_sms), cells / (double)d.h_cycles[k]);
             }
         }

@@ -76,7 +76,8 @@ struct U16Params {
     uint64_t         bound_col0;
     int              gap_open_extend, gap_extend;
     uint32_t        *chunk_counter;
-    uint32_t         static_first;   // chunk groups dealt statically before the counter is used (set by the launcher)
+    uint32_t         static_first;   // deal every warp's first chunk statically (set by the launcher: few chunks per warp)
+    uint32_t         express_ctas;   // CTAs that give the longest chunks a scheduler each (0 = none)
     unsigned long long *cycle_acc;   // sum over CTAs of their elapsed clock64 cycles (one CTA per SM), or nullptr
 };
 int osw_launch_u16(const U16Params &p, const OswPass &pass, int n_sms, cudaStream_t st);

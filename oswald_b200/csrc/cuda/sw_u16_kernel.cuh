@@ -239,16 +239,30 @@ sw_u16_kernel(const KArgs a) {
     const uint32_t emit = ((fa & OSW_LANE_EMIT) && a.lane[0][t].q_len ? 1u : 0u) | ((fb & OSW_LANE_EMIT) && a.lane[1][t].q_len ? 2u : 0u);
     const uint32_t last_mask = emit ? OSW_COL_LAST : 0u;
 
-    // On a database of only a few chunks per warp the first chunks are dealt statically, warp w of
-    // CTA b taking group w * gridDim.x + b of the (descending) chunk list: every SM starts with the
-    // same mix of long and short chunks (measured + 2..6 % there, - 2.4 % on a large database, where
-    // the counter alone is used).  Later chunks come from the counter.
-    bool first_fetch = p.static_first != 0;
+    // Chunk hand-out.  Later chunks always come from a counter (longest first); the FIRST chunk of a
+    // warp can be dealt statically:
+    //  * express CTAs (p.express_ctas = K > 0; chosen by the host when the launch would last as long
+    //    as its longest chunk): the 4K longest chunk groups go to warps 0-3 of CTAs 0..K-1, one warp
+    //    per scheduler, and the other warps of those CTAs retire at once - a warp alone on its
+    //    scheduler walks its columns at the latency of one step instead of sharing the issue slots
+    //    with three others;
+    //  * on a database of only a few chunks per warp (p.static_first) warp w of CTA b takes group
+    //    w * CTAs + b of the remaining list, so that every SM starts with the same mix of long and
+    //    short chunks (measured + 2..6 % there, - 2.4 % on a large database, which uses the counter).
+    const uint32_t K = p.express_ctas < gridDim.x ? p.express_ctas : 0u;
+    const uint32_t express_groups = 4u * K;
+    const bool express = blockIdx.x < K;
+    if (express && wib >= 4) return;
+    const uint32_t dealt = express_groups + (p.static_first ? (gridDim.x - K) * WARPS : 0u);       // groups not taken from the counter
+    bool first_fetch = express || p.static_first != 0;
     for (;;) {
         // ---- fetch one chunk per group ---------------------------------------------------
-        if (lane == 0)
-            s_chunk[wib] = first_fetch ? (uint32_t)(wib * gridDim.x + blockIdx.x) * GROUPS
-                                       : p.static_first + atomicAdd(p.chunk_counter, (uint32_t)GROUPS);
+        if (lane == 0) {
+            uint32_t g;
+            if (first_fetch) g = express ? wib * K + blockIdx.x : express_groups + wib * (gridDim.x - K) + (blockIdx.x - K);
+            else g = dealt + atomicAdd(p.chunk_counter, 1u);
+            s_chunk[wib] = g * GROUPS;
+        }
         first_fetch = false;
         __syncwarp();
         const uint32_t cbase = p.chunk_first + s_chunk[wib];
@@ -464,7 +478,7 @@ int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
     }
     KArgs k = a;
     const uint32_t slots = (uint32_t)n_sms * (THREADS / 32) * (32 / G);          // chunks in flight
-    k.p.static_first = a.p.chunk_end - a.p.chunk_first < 12 * slots ? slots : 0u;
+    k.p.static_first = a.p.chunk_end - a.p.chunk_first < 12 * slots ? 1u : 0u;
     profile_build_kernel<G, R, PD><<<32, 256, 0, st>>>(k);
     sw_u16_kernel<G, R, THREADS, PD><<<n_sms, THREADS, smem, st>>>(k);
     return cudaGetLastError() == cudaSuccess ? OSW_OK : OSW_E_CUDA;
