@@ -503,7 +503,9 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             if (end > first && !getenv("OSW_NO_EXPRESS")) {
                 const LaunchModel m(ps.G, ps.R, pd, (double)cols, d.n_sms);
                 const double longest = (double)chunk_cols(first);
-                if (longest * m.contended > 1.5 * m.t_pipe) {
+                double ratio = 1.5;
+                if (const char *e = getenv("OSW_EXPRESS_RATIO")) ratio = atof(e);        // experiments
+                if (longest * m.contended > ratio * m.t_pipe) {
                     const double cut = longest * m.alone / m.contended;      // shorter chunks finish in time anyway
                     uint32_t n = 0;
                     while (first + n < end && n < 64u * m.groups && (double)chunk_cols(first + n) > cut) ++n;
