@@ -221,6 +221,12 @@ def main():
     if args.gpus > 1 and world == 1:
         raise SystemExit("bench.py: for N > 1 launch with torch.distributed.run (one rank per GPU)")
 
+    # stdout carries exactly one JSON line: native libraries that print there (NCCL announces its
+    # version on stdout when the first communicator is made) are sent to stderr instead
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import oswald_b200 as ob
     from oswald_b200.host import calibrate, merge_hits
@@ -354,7 +360,8 @@ def main():
             out["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": cores, "kind": kind, "seconds": secs,
                                    "sample": "%d queries (sum %d) x %d-sequence / %d-residue sample of the same synthetic database" % (
                                        queries.n, q_total, len(seqs), sum(len(x) for x in seqs))}
-        print(json.dumps(out))
+        json_out.write(json.dumps(out) + "\n")
+        json_out.flush()
     s.close()
     if dist is not None:
         dist.barrier()
