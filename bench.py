@@ -200,7 +200,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seqs-per-gpu", type=int, default=SEQS_PER_GPU)
-    ap.add_argument("--ref-sample", type=int, default=20000, help="sequences in the CPU baseline's sample")
+    ap.add_argument("--ref-sample", type=int, default=100000, help="sequences in the CPU baseline's sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels", type=int, default=3, help="kernel mask (1|2 = default, 2 = 32-bit only)")
     ap.add_argument("--chunk-cols", type=int, default=0, help="residues per chunk (0 = library default)")
