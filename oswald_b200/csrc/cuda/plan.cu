@@ -5,7 +5,7 @@
 // half), balanced by rows; on a track the queries follow each other, each starting on a lane
 // boundary.  A pass covers the next G*R rows of both tracks.  Compared with pairing queries
 // one-to-one, nothing is lost when the two queries of a pair differ in length, and short
-// queries ride in the same wide (G = 32, R = 44) launches as long ones.
+// queries ride in the same full-width (G = 32, R = 40) launches as long ones.
 #include "osw_internal.h"
 #include <algorithm>
 #include <stdlib.h>
