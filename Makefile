@@ -38,10 +38,14 @@ tools/osw_synth: tools/osw_synth.c
 tools/libosw_synth.so: tools/osw_synth.c
 	$(HOSTCC) -O2 -fopenmp -fPIC -shared -DOSW_SYNTH_NO_MAIN -o $@ $< -lm
 
+# experiment: dependent-issue latency of the DPX instructions (not part of `all`)
+tools/dpx_latency: tools/dpx_latency.cu
+	$(NVCC) $(ARCH) -O3 -o $@ $<
+
 oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -rf build oswald_b200/liboswald_cuda.so oswald_b200/oswald tools/osw_synth tools/libosw_synth.so
+	rm -rf build oswald_b200/liboswald_cuda.so oswald_b200/oswald tools/osw_synth tools/libosw_synth.so tools/dpx_latency
 	$(MAKE) -C oracle clean
 .PHONY: all lib cli tools oracle clean
