@@ -54,6 +54,7 @@ struct DevState {
     int2 *d_scratch = nullptr; size_t scratch_cap = 0;
     uint2 *d_bound = nullptr; size_t bound_cap = 0;   // bottom rows handed from pass to pass (in place), one segment of chunks at a time
     unsigned char *d_profile = nullptr;        // the current pass's profile table image
+    uint32_t *d_first_table = nullptr;         // the current pass's first-chunk deal (CTAs x warps)
     uint2 *d_pairs = nullptr; uint32_t pairs_cap = 0;
     uint32_t *d_counters = nullptr;            // [0] flagged count, [1..] chunk counters per launch
     unsigned long long *d_task_counter = nullptr;   // [0] i32 queue, [1] n_tasks mirror
@@ -210,6 +211,7 @@ extern "C" int osw_init(int n_devices, const int *devices, osw_ctx **out) {
         }
         if ((e = cudaMalloc(&d.d_matrix, 24 * 32)) != cudaSuccess ||
             (e = cudaMalloc(&d.d_profile, OSW_PROFILE_BYTES)) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_first_table, 1024 * 16 * sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_counters, (1 + MAX_LAUNCH_SLOTS) * sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_task_counter, 2 * sizeof(unsigned long long))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_cycles, MAX_LAUNCH_SLOTS * sizeof(unsigned long long))) != cudaSuccess ||
@@ -231,7 +233,7 @@ extern "C" void osw_free(osw_ctx *c) {
         if (d.st) cudaStreamSynchronize(d.st);
         free_db(d);
         cudaFree(d.d_scores); cudaFree(d.d_queries); cudaFree(d.d_qoff); cudaFree(d.d_matrix); cudaFree(d.d_scratch);
-        cudaFree(d.d_profile);
+        cudaFree(d.d_profile); cudaFree(d.d_first_table);
         cudaFree(d.d_pairs); cudaFree(d.d_counters); cudaFree(d.d_task_counter); cudaFree(d.d_cycles);
         cudaFree(d.topr.hist); cudaFree(d.topr.prefix); cudaFree(d.topr.remaining); cudaFree(d.topr.out_count); cudaFree(d.topr.out_keys);
         if (d.h_keys) cudaFreeHost(d.h_keys);
@@ -513,7 +515,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
                 }
             }
             up.queries = d.d_queries; up.q_off = d.d_qoff; up.matrix = d.d_matrix;
-            up.profile = d.d_profile;
+            up.profile = d.d_profile; up.first_table = d.d_first_table; up.dyn_base = 0;
             up.scores = d.d_scores; up.n_seqs = N;
             up.bound = d.d_bound; up.bound_col0 = bound_col0;
             up.gap_open_extend = go + ge; up.gap_extend = ge;

@@ -107,7 +107,10 @@ struct KArgs {
     uint32_t nge2;           // (-ge) & 0xffff, both halves
     uint32_t ngoe_word;      // -(goe | goe<<16) as a 32-bit two's complement
     uint32_t bias;           // B
+    uint32_t n_ctas, warps;  // launch geometry of the scoring kernel (for the first-chunk deal)
 };
+
+constexpr uint32_t NO_GROUP = 0x0fffffffu;       // deal-table entry of a warp that takes no chunk
 
 // One 16-byte profile entry (4 rows x one residue) - and its high-half twin in pair-database mode -
 // written at its place in a table image starting at `base` (shared or global memory).
@@ -155,6 +158,28 @@ __global__ void __launch_bounds__(256) profile_build_kernel(const KArgs a) {
     const int n = prof_copies(G) * 24 * prof_quads(G, R);
     for (int idx = blockIdx.x * 256 + threadIdx.x; idx < n; idx += gridDim.x * 256)
         profile_entry<G, R, PD>(idx, a, s_mat, a.p.profile);
+    // The first chunk group of every warp of the scoring kernel, when the launcher asked for a
+    // static deal (a.p.first_table != nullptr):
+    //  * express CTAs (K = a.p.express_ctas > 0; chosen by the host when the launch would last as
+    //    long as its longest chunk): the 4K longest chunk groups go to warps 0-3 of CTAs 0..K-1, one
+    //    warp per scheduler, and the other warps of those CTAs take nothing - a warp alone on its
+    //    scheduler walks its columns at the latency of one step instead of sharing the issue slots
+    //    with three others;
+    //  * on a database of only a few chunks per warp (a.p.static_first) warp w of CTA b takes group
+    //    w * CTAs + b of the remaining list, so that every SM starts with the same mix of long and
+    //    short chunks (measured + 2..6 % there, - 2.4 % on a large database, which uses the counter);
+    //  * every other warp starts at the counter like later fetches do (entry = NO_GROUP + 1).
+    if (a.p.first_table && blockIdx.x == 0) {
+        const uint32_t K = min(a.p.express_ctas, a.n_ctas - 1);
+        for (uint32_t i = threadIdx.x; i < a.n_ctas * a.warps; i += 256) {
+            const uint32_t b = i / a.warps, w = i % a.warps;
+            uint32_t g;
+            if (b < K) g = w < 4 ? w * K + b : NO_GROUP;
+            else if (a.p.static_first) g = 4u * K + w * (a.n_ctas - K) + (b - K);
+            else g = NO_GROUP + 1;
+            a.p.first_table[i] = g;
+        }
+    }
 }
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier --------------------------------
@@ -180,7 +205,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 // PD = "pair database" mode: both halves work on the SAME query rows (track 0) against two
 // different database sequences zipped in the pair stream; the score word of a row is the sum of a
 // low-half table entry (first sequence's residue) and a high-half table entry (second one's).
-template <int G, int R, int THREADS, bool PD>
+// DEAL = the first chunk of every warp comes from the deal table (express CTAs).  A template flag
+// rather than a run-time test: the R = 40 row sweep uses every register it can get, and even a few
+// more instructions in the fetch path changed the schedule of the sweep (- 0.8..1.7 % at config 2).
+template <int G, int R, int THREADS, bool PD, bool DEAL>
 __global__ void __launch_bounds__(THREADS, 1)
 sw_u16_kernel(const KArgs a) {
     constexpr int WARPS = THREADS / 32;
@@ -239,29 +267,22 @@ sw_u16_kernel(const KArgs a) {
     const uint32_t emit = ((fa & OSW_LANE_EMIT) && a.lane[0][t].q_len ? 1u : 0u) | ((fb & OSW_LANE_EMIT) && a.lane[1][t].q_len ? 2u : 0u);
     const uint32_t last_mask = emit ? OSW_COL_LAST : 0u;
 
-    // Chunk hand-out.  Later chunks always come from a counter (longest first); the FIRST chunk of a
-    // warp can be dealt statically:
-    //  * express CTAs (p.express_ctas = K > 0; chosen by the host when the launch would last as long
-    //    as its longest chunk): the 4K longest chunk groups go to warps 0-3 of CTAs 0..K-1, one warp
-    //    per scheduler, and the other warps of those CTAs retire at once - a warp alone on its
-    //    scheduler walks its columns at the latency of one step instead of sharing the issue slots
-    //    with three others;
-    //  * on a database of only a few chunks per warp (p.static_first) warp w of CTA b takes group
-    //    w * CTAs + b of the remaining list, so that every SM starts with the same mix of long and
-    //    short chunks (measured + 2..6 % there, - 2.4 % on a large database, which uses the counter).
-    const uint32_t K = p.express_ctas < gridDim.x ? p.express_ctas : 0u;
-    const uint32_t express_groups = 4u * K;
-    const bool express = blockIdx.x < K;
-    if (express && wib >= 4) return;
-    const uint32_t dealt = express_groups + (p.static_first ? (gridDim.x - K) * WARPS : 0u);       // groups not taken from the counter
-    bool first_fetch = express || p.static_first != 0;
+    // Chunk hand-out: from a counter, longest first.  A warp's FIRST chunk can be dealt statically:
+    // by position on a database of only a few chunks per warp (p.static_first = chunks dealt that
+    // way: warp w of CTA b takes group w * CTAs + b), or through the table profile_build_kernel
+    // fills when there are express CTAs (DEAL; see there).
+    bool first_fetch = DEAL || p.static_first != 0;
     for (;;) {
         // ---- fetch one chunk per group ---------------------------------------------------
-        if (lane == 0) {
-            uint32_t g;
-            if (first_fetch) g = express ? wib * K + blockIdx.x : express_groups + wib * (gridDim.x - K) + (blockIdx.x - K);
-            else g = dealt + atomicAdd(p.chunk_counter, 1u);
-            s_chunk[wib] = g * GROUPS;
+        if (DEAL) {
+            if (lane == 0) {
+                uint32_t g = first_fetch ? p.first_table[blockIdx.x * WARPS + wib] : NO_GROUP + 1;
+                if (g > NO_GROUP) g = p.dyn_base + atomicAdd(p.chunk_counter, 1u);
+                s_chunk[wib] = g * GROUPS;
+            }
+        } else {
+            if (lane == 0) s_chunk[wib] = first_fetch ? (uint32_t)(wib * gridDim.x + blockIdx.x) * GROUPS
+                                                      : p.static_first + atomicAdd(p.chunk_counter, (uint32_t)GROUPS);
         }
         first_fetch = false;
         __syncwarp();
@@ -463,25 +484,41 @@ sw_u16_kernel(const KArgs a) {
     if (p.cycle_acc && threadIdx.x == 0) atomicAdd(p.cycle_acc, (unsigned long long)(clock64() - clk0));
 }
 
-template <int G, int R, int THREADS, bool PD>
-int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
-    const size_t prof = (prof_copy_bytes(G, R) * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0)) * (PD ? 2 : 1);
-    const size_t smem = prof + (size_t)(THREADS / 32) * 32 * 16 + (size_t)(THREADS / 32) * (32 / G) * RING * 16 + (size_t)(THREADS / 32) * 32 * 8;
+template <int G, int R, int THREADS, bool PD, bool DEAL>
+int launch_kernel(const KArgs &k, int n_sms, size_t smem, cudaStream_t st) {
     static bool configured[64] = {};          // the attribute is per device
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return OSW_E_CUDA;
     if (dev < 0 || dev >= 64 || !configured[dev]) {
         if (smem > 227 * 1024) return OSW_E_ARG;
-        if (cudaFuncSetAttribute(sw_u16_kernel<G, R, THREADS, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(sw_u16_kernel<G, R, THREADS, PD, DEAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return OSW_E_CUDA;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    KArgs k = a;
-    const uint32_t slots = (uint32_t)n_sms * (THREADS / 32) * (32 / G);          // chunks in flight
-    k.p.static_first = a.p.chunk_end - a.p.chunk_first < 12 * slots ? 1u : 0u;
     profile_build_kernel<G, R, PD><<<32, 256, 0, st>>>(k);
-    sw_u16_kernel<G, R, THREADS, PD><<<n_sms, THREADS, smem, st>>>(k);
+    sw_u16_kernel<G, R, THREADS, PD, DEAL><<<n_sms, THREADS, smem, st>>>(k);
     return cudaGetLastError() == cudaSuccess ? OSW_OK : OSW_E_CUDA;
+}
+
+template <int G, int R, int THREADS, bool PD>
+int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
+    const size_t prof = (prof_copy_bytes(G, R) * prof_copies(G) + (prof_copies(G) > 1 ? 128 : 0)) * (PD ? 2 : 1);
+    const size_t smem = prof + (size_t)(THREADS / 32) * 32 * 16 + (size_t)(THREADS / 32) * (32 / G) * RING * 16 + (size_t)(THREADS / 32) * 32 * 8;
+    KArgs k = a;
+    constexpr uint32_t WARPS = THREADS / 32;
+    const uint32_t slots = (uint32_t)n_sms * WARPS * (32 / G);          // chunks in flight
+    const bool few_chunks = a.p.chunk_end - a.p.chunk_first < 12 * slots;
+    const uint32_t K = std::min<uint32_t>(a.p.express_ctas, (uint32_t)n_sms - 1);
+    k.n_ctas = (uint32_t)n_sms; k.warps = WARPS;
+    if (K) {            // express CTAs (and, with few chunks per warp, a static deal for the others) through the table
+        k.p.express_ctas = K;
+        k.p.static_first = few_chunks ? 1u : 0u;
+        k.p.dyn_base = 4u * K + (few_chunks ? ((uint32_t)n_sms - K) * WARPS : 0u);       // groups dealt statically
+        return launch_kernel<G, R, THREADS, PD, true>(k, n_sms, smem, st);
+    }
+    k.p.first_table = nullptr;
+    k.p.static_first = few_chunks ? slots : 0u;          // chunks dealt by position
+    return launch_kernel<G, R, THREADS, PD, false>(k, n_sms, smem, st);
 }
 
 // CTA size: 512 threads (128 registers each) up to R = 32, 384 (168 registers) above.
