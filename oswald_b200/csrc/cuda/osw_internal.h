@@ -76,7 +76,7 @@ struct U16Params {
     uint64_t         bound_col0;
     int              gap_open_extend, gap_extend;
     uint32_t        *chunk_counter;
-    uint32_t         static_first;   // deal every warp's first chunk statically (set by the launcher: few chunks per warp)
+    uint32_t         static_first;   // deal every warp's first chunk statically, through the table (set by the launcher: few chunks per warp)
     uint32_t         express_ctas;   // CTAs that give the longest chunks a scheduler each (0 = none)
     uint32_t        *first_table;    // [CTAs x warps] first chunk group of every warp (filled by profile_build_kernel), >= 148 * 16 entries
     uint32_t         dyn_base;       // first group handed out by the counter (set by the launcher)

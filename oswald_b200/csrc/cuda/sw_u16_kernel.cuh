@@ -205,9 +205,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 // PD = "pair database" mode: both halves work on the SAME query rows (track 0) against two
 // different database sequences zipped in the pair stream; the score word of a row is the sum of a
 // low-half table entry (first sequence's residue) and a high-half table entry (second one's).
-// DEAL = the first chunk of every warp comes from the deal table (express CTAs).  A template flag
-// rather than a run-time test: the R = 40 row sweep uses every register it can get, and even a few
-// more instructions in the fetch path changed the schedule of the sweep (- 0.8..1.7 % at config 2).
+// DEAL = the first chunk of every warp comes from the deal table (express CTAs, small databases).
+// A template flag rather than a run-time test: the R = 40 row sweep uses every register it can
+// get, and even a loop-carried flag in the fetch path changed the schedule ptxas finds for the
+// sweep (- 0.8..1.7 % at config 2, measured against the previous build on the same box).
 template <int G, int R, int THREADS, bool PD, bool DEAL>
 __global__ void __launch_bounds__(THREADS, 1)
 sw_u16_kernel(const KArgs a) {
@@ -267,11 +268,9 @@ sw_u16_kernel(const KArgs a) {
     const uint32_t emit = ((fa & OSW_LANE_EMIT) && a.lane[0][t].q_len ? 1u : 0u) | ((fb & OSW_LANE_EMIT) && a.lane[1][t].q_len ? 2u : 0u);
     const uint32_t last_mask = emit ? OSW_COL_LAST : 0u;
 
-    // Chunk hand-out: from a counter, longest first.  A warp's FIRST chunk can be dealt statically:
-    // by position on a database of only a few chunks per warp (p.static_first = chunks dealt that
-    // way: warp w of CTA b takes group w * CTAs + b), or through the table profile_build_kernel
-    // fills when there are express CTAs (DEAL; see there).
-    bool first_fetch = DEAL || p.static_first != 0;
+    // Chunk hand-out: from a counter, longest first.  With DEAL a warp's FIRST chunk comes from the
+    // table profile_build_kernel fills (express CTAs; small databases: see there).
+    bool first_fetch = DEAL;
     for (;;) {
         // ---- fetch one chunk per group ---------------------------------------------------
         if (DEAL) {
@@ -280,11 +279,10 @@ sw_u16_kernel(const KArgs a) {
                 if (g > NO_GROUP) g = p.dyn_base + atomicAdd(p.chunk_counter, 1u);
                 s_chunk[wib] = g * GROUPS;
             }
+            first_fetch = false;
         } else {
-            if (lane == 0) s_chunk[wib] = first_fetch ? (uint32_t)(wib * gridDim.x + blockIdx.x) * GROUPS
-                                                      : p.static_first + atomicAdd(p.chunk_counter, (uint32_t)GROUPS);
+            if (lane == 0) s_chunk[wib] = atomicAdd(p.chunk_counter, (uint32_t)GROUPS);
         }
-        first_fetch = false;
         __syncwarp();
         const uint32_t cbase = p.chunk_first + s_chunk[wib];
         __syncwarp();
@@ -510,14 +508,13 @@ int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
     const bool few_chunks = a.p.chunk_end - a.p.chunk_first < 12 * slots;
     const uint32_t K = std::min<uint32_t>(a.p.express_ctas, (uint32_t)n_sms - 1);
     k.n_ctas = (uint32_t)n_sms; k.warps = WARPS;
-    if (K) {            // express CTAs (and, with few chunks per warp, a static deal for the others) through the table
+    if (K || few_chunks) {          // express CTAs and / or a static first deal: through the table
         k.p.express_ctas = K;
         k.p.static_first = few_chunks ? 1u : 0u;
         k.p.dyn_base = 4u * K + (few_chunks ? ((uint32_t)n_sms - K) * WARPS : 0u);       // groups dealt statically
         return launch_kernel<G, R, THREADS, PD, true>(k, n_sms, smem, st);
     }
-    k.p.first_table = nullptr;
-    k.p.static_first = few_chunks ? slots : 0u;          // chunks dealt by position
+    k.p.first_table = nullptr;          // large database: the counter alone
     return launch_kernel<G, R, THREADS, PD, false>(k, n_sms, smem, st);
 }
 
