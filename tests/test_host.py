@@ -3,7 +3,9 @@ the chunk-stream builder, the host mirror (preprocess / query loading), hit merg
 executable model of the 16-bit kernel's dataflow against the oracle.  No GPU calls."""
 import ctypes as C
 import os
+import json
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -366,3 +368,22 @@ def test_cli_rejects_too_long_sequences(built, tmp_path):
     (tmp_path / "in.fasta").write_text(">long\n" + "A" * 65536 + "\n")
     r = subprocess.run([_cli(), "-O", "preprocess", "-i", "in.fasta", "-o", "db"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode != 0 and "65535" in r.stdout
+
+
+def test_scoring_kernel_schedule_is_the_measured_one(built):
+    """The row sweep's SASS schedule is sensitive to changes elsewhere in the kernel (0.8 % and 1.7 %
+    at config 2 were lost that way, unnoticed behind box-to-box spread).  The inner loops of the
+    instances the big workloads run must be the ones that were measured; if this fails after a
+    deliberate kernel change, re-measure against the previous build on ONE box (tools/build_at.sh,
+    tools/gpu_ab.sh) and refresh the golden file with `python tools/kernel_schedule.py --update`."""
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import kernel_schedule
+    got = kernel_schedule.fingerprints(capi.LIB_PATH)
+    want = json.load(open(kernel_schedule.GOLDEN))
+    for name, fp in want.items():
+        assert got[name]["local_memory_ops"] == 0, name
+        assert got[name]["viaddmnmx_u16x2"] == fp["viaddmnmx_u16x2"] and got[name]["vimnmx3_u16x2"] == fp["vimnmx3_u16x2"], name
+        assert got[name] == fp, "%s: inner loop changed (%s -> %s)" % (name, fp, got[name])

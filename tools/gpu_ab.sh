@@ -1,21 +1,26 @@
 #!/bin/bash
-# A/B on one box of an environment switch (default: OSW_NO_EXPRESS=1 as the baseline arm).
-# usage: bash tools/gpu_ab.sh <tag> [VAR=value of the baseline arm]
-TAG=${1:-ab}; BASE=${2:-OSW_NO_EXPRESS=1}; NEW=${3:-OSW_DUMMY=1}
+# A/B of two builds (or of an environment switch) on ONE box: box-to-box spread is about 3 %, the
+# steps worth finding are below 1 %.   usage (under gpurun):
+#   bash tools/gpu_ab.sh <tag> <baseline.so | VAR=value> [bench arguments ...]
+# baseline.so: a library from tools/build_at.sh, loaded through OSWALD_CUDA_LIB; VAR=value: an
+# environment switch of the library set for the baseline arm only.
+TAG=${1:-ab}; BASE=${2:?baseline}; shift 2
+case "$BASE" in *.so) BASE="OSWALD_CUDA_LIB=$(readlink -f "$BASE")";; esac
 mkdir -p gpurun_out
 run() {
   local label=$1; shift
-  for V in base new; do
-    if [ $V = base ]; then PRE="env $BASE"; else PRE="env $NEW"; fi
-    OSW_TRACE=1 timeout 300 $PRE python bench.py --no-cpu-baseline "$@" 2> gpurun_out/${TAG}.err | python -c "
+  for rep in 1 2; do
+    for V in new base; do
+      if [ $V = base ]; then PRE="env $BASE"; else PRE="env"; fi
+      OSW_TRACE=1 timeout 300 $PRE python bench.py --no-cpu-baseline "$@" 2> gpurun_out/${TAG}.err | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('$label $V: %.1f GCUPS  score %.3f ms  busy-clk %.2f' % (d['value'], d['breakdown_ms']['score'], d['roofline']['achieved_cells_per_busy_sm_clk']))"
-    grep "osw trace" gpurun_out/${TAG}.err | tail -1 | cut -c1-110
+d=json.loads(sys.stdin.read()); print('$label $V: %.1f GCUPS  e2e %.1f  score %.3f ms  busy-clk %.2f' % (d['value'], d['e2e']['value'], d['breakdown_ms']['score'], d['roofline']['achieved_cells_per_busy_sm_clk']))"
+    done
   done
 }
-run c1 --steps 5 --warmup 3 --seqs-per-gpu 10000 --query-lengths 144
-run s50k_4q --steps 5 --warmup 3 --seqs-per-gpu 50000 --query-lengths 144,189,222,375
-run s100k --steps 3 --warmup 2 --seqs-per-gpu 100000 --query-lengths 144
-run s100k_375 --steps 3 --warmup 2 --seqs-per-gpu 100000 --query-lengths 375
-run s200k --steps 3 --warmup 2 --seqs-per-gpu 200000 --query-lengths 144
+if [ $# -gt 0 ]; then run custom "$@"; exit 0; fi
+run c2 --steps 3 --warmup 2
+run q5478 --steps 2 --warmup 1 --query-lengths 5478
 run q144 --steps 2 --warmup 1 --query-lengths 144
+run c1 --steps 5 --warmup 3 --seqs-per-gpu 10000 --query-lengths 144
+run s100k --steps 3 --warmup 2 --seqs-per-gpu 100000 --query-lengths 144
