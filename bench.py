@@ -189,7 +189,7 @@ def workload_config(n_gpus, seqs_per_gpu):
     return {"workload": "config 2 (Swiss-Prot-sized synthetic DB per GPU, 20 queries 144-5478, BLOSUM62 10/2, top 10)",
             "sequences": seqs_per_gpu * n_gpus, "length_distribution": "log-normal mu=%.3f sigma=%.1f clipped [10,65535]" % (MU, SIGMA),
             "query_lengths": QUERY_LENGTHS, "matrix": MATRIX, "gap_open": GAP_OPEN, "gap_extend": GAP_EXTEND, "top": TOP,
-            "sharding": "chunks of ~8192 residues (2048 for the shortest sequences) dealt round-robin to %d GPU(s)" % n_gpus,
+            "sharding": "chunks of ~8192 residues (2048 and 512 for the shortest sequences, taken last) dealt round-robin to %d GPU(s)" % n_gpus,
             "l2": "inputs larger than L2 (database stream >= 200 MB per GPU, score matrix 45 MB)"}
 
 

@@ -6,7 +6,7 @@
  * The canonical database (stable ascending length order, sequences.c:1130-1225) is cut into
  * CHUNKS of consecutive whole sequences holding about `chunk_cols` residues each (one longer
  * sequence is a chunk of its own; the chunks of the shortest sequences, which the GPU takes last,
- * are a quarter of that size to even out the end of a launch).  Because the order is by length, a chunk is a length bin:
+ * are a quarter and then a sixteenth of that size to even out the end of a launch).  Because the order is by length, a chunk is a length bin:
  * all its sequences have (nearly) the same length.  A chunk is stored as a COLUMN STREAM, one
  * byte per residue:
  *      bits 0-4  residue code 0..23
