@@ -14,7 +14,7 @@ CLISRC   := $(filter-out $(HOSTLIB),$(wildcard oswald_b200/csrc/host/*.c))
 
 all: lib cli tools oracle
 
-lib: oswald_b200/liboswald_cuda.so
+lib: oswald_b200/liboswald_cuda.so oswald_b200/build_tag.txt
 cli: oswald_b200/oswald
 tools: tools/osw_synth tools/libosw_synth.so
 
@@ -28,6 +28,12 @@ build/%.o: oswald_b200/csrc/host/%.c $(wildcard oswald_b200/csrc/host/*.h) oswal
 
 oswald_b200/liboswald_cuda.so: $(CUOBJ) build/dbformat.o build/submat.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart_static -lpthread -ldl -lrt -lgomp
+
+# hash of the kernel and layout sources the library was built from: bench.py reports it as `build`
+# and matches it against the tag stored with profiles/ncu_traffic.json
+oswald_b200/build_tag.txt: oswald_b200/liboswald_cuda.so
+	cat $(sort $(CUSRC)) oswald_b200/csrc/cuda/*.h oswald_b200/csrc/cuda/*.cuh oswald_b200/csrc/host/dbformat.c oswald_b200/csrc/host/dbformat.h \
+	    | sha256sum | cut -c1-12 > $@
 
 oswald_b200/oswald: $(CLISRC) oswald_b200/liboswald_cuda.so
 	$(HOSTCC) -O2 -std=gnu11 -Wall -fopenmp -Iinclude -Ioswald_b200/csrc/host -o $@ $(CLISRC) \
@@ -46,6 +52,6 @@ oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -rf build oswald_b200/liboswald_cuda.so oswald_b200/oswald tools/osw_synth tools/libosw_synth.so tools/dpx_latency
+	rm -rf build oswald_b200/liboswald_cuda.so oswald_b200/build_tag.txt oswald_b200/oswald tools/osw_synth tools/libosw_synth.so tools/dpx_latency
 	$(MAKE) -C oracle clean
 .PHONY: all lib cli tools oracle clean

@@ -39,6 +39,9 @@ struct DevState {
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     uint8_t *d_stage = nullptr; size_t stage_cap = 0;         // sequences gathered for the 32-bit re-score (streaming mode)
     uint64_t *d_task_off = nullptr; size_t task_off_cap = 0;
+    uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;       // pinned staging of the same (kept until the next search)
+    uint64_t *h_task_off = nullptr; size_t h_task_off_cap = 0;
+    uint2 *h_pairs = nullptr; size_t h_pairs_cap = 0;
     cudaEvent_t ev[6] = {};
     // database shard
     osw_shard shard = {};
@@ -123,7 +126,33 @@ double now_ms() {
 
 }  // namespace
 
+// Experiment / test switches, read from the environment ONCE, in osw_init: the
+// search path itself never calls getenv.  None of them changes a result.
+struct Tunables {
+    uint32_t chunk_cols = 0;            // OSW_CHUNK_COLS: residues per chunk (0 = by database size)
+    size_t   bound_budget_cols = (size_t)2 << 30;   // OSW_BOUND_BUDGET_COLS: bottom-row buffer, columns (16 GiB)
+    uint64_t score_budget = (uint64_t)8 << 30;      // OSW_SCORE_BUDGET_KB: score matrix per batch of queries
+    uint32_t flag_cap = 0;              // OSW_FLAG_CAP: capacity of the flagged-pair list (0 = by problem size)
+    bool     express = true;            // OSW_NO_EXPRESS
+    double   express_ratio = 1.5;       // OSW_EXPRESS_RATIO
+    int      force_g = 0;               // OSW_MIN_G: force a group width for single-pass plans
+    int      rmax = 0;                  // OSW_RMAX: rows per lane of the full-height passes (0 = default)
+    bool     trace = false;             // OSW_TRACE: per-launch report on stderr
+    void read() {
+        if (const char *e = getenv("OSW_CHUNK_COLS")) { const int v = atoi(e); if (v >= 64) chunk_cols = (uint32_t)v; }
+        if (const char *e = getenv("OSW_BOUND_BUDGET_COLS")) { const long long v = atoll(e); if (v >= 1024) bound_budget_cols = (size_t)v; }
+        if (const char *e = getenv("OSW_SCORE_BUDGET_KB")) { const long long v = atoll(e); if (v >= 1) score_budget = (uint64_t)v << 10; }
+        if (const char *e = getenv("OSW_FLAG_CAP")) { const long long v = atoll(e); if (v >= 1) flag_cap = (uint32_t)v; }
+        express = getenv("OSW_NO_EXPRESS") == nullptr;
+        if (const char *e = getenv("OSW_EXPRESS_RATIO")) express_ratio = atof(e);
+        if (const char *e = getenv("OSW_MIN_G")) force_g = atoi(e);
+        if (const char *e = getenv("OSW_RMAX")) rmax = atoi(e);
+        trace = getenv("OSW_TRACE") != nullptr;
+    }
+};
+
 struct osw_ctx {
+    Tunables tune;
     int n_dev = 0;
     DevState *devs = nullptr;
     int kernel_mask = OSW_K_DEFAULT;
@@ -184,6 +213,7 @@ extern "C" int osw_init(int n_devices, const int *devices, osw_ctx **out) {
     c->devs = new (std::nothrow) DevState[n_devices];
     if (!c->devs) { delete c; return OSW_E_NOMEM; }
     c->n_dev = n_devices;
+    c->tune.read();
     for (int i = 0; i < n_devices; ++i) {
         DevState &d = c->devs[i];
         d.dev = devices ? devices[i] : i;
@@ -244,6 +274,9 @@ extern "C" void osw_free(osw_ctx *c) {
         for (int k = 0; k < 2; ++k) { if (d.ev_ready[k]) cudaEventDestroy(d.ev_ready[k]); if (d.ev_free[k]) cudaEventDestroy(d.ev_free[k]); }
         if (d.st_copy) cudaStreamDestroy(d.st_copy);
         cudaFree(d.d_stage); cudaFree(d.d_task_off);
+        if (d.h_stage) cudaFreeHost(d.h_stage);
+        if (d.h_task_off) cudaFreeHost(d.h_task_off);
+        if (d.h_pairs) cudaFreeHost(d.h_pairs);
         if (d.st) cudaStreamDestroy(d.st);
     }
     delete[] c->devs;
@@ -269,6 +302,18 @@ extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *
     if (!c || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return OSW_E_ARG;
     if (n_seqs && (!residues || !offsets)) return OSW_E_ARG;
     if (n_seqs > 0xffffffffull) return OSW_E_ARG;
+    // The layout and the kernels rely on the canonical order (sequences.c:1130-1225): lengths
+    // ascending (a chunk's last sequence is its longest; empty sequences lead), offsets monotonic.
+    for (uint64_t i = 0, prev = 0; i < n_seqs; ++i) {
+        if (offsets[i + 1] < offsets[i]) { snprintf(g_err, sizeof g_err, "database offsets decrease at sequence %llu", (unsigned long long)i); return OSW_E_ARG; }
+        const uint64_t len = offsets[i + 1] - offsets[i];
+        if (len < prev || len > 0x7fffffffull) {
+            snprintf(g_err, sizeof g_err, "database sequence %llu (length %llu) breaks the ascending-length order",
+                     (unsigned long long)i, (unsigned long long)len);
+            return OSW_E_ARG;
+        }
+        prev = len;
+    }
     // Work-unit size: 8192 residues for large databases (0.8 % pipeline fill per chunk; measured
     // best together with the quarter-size chunks at the end of the queue); smaller for small
     // databases so that every group of lanes on every SM gets several chunks.
@@ -278,7 +323,7 @@ extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *
         const uint64_t fit = per_dev / 25000;            // ~ 148 SMs x 12 warps x 8 groups x 2
         if (fit < chunk_cols) chunk_cols = (uint32_t)(fit < 256 ? 256 : fit);
     }
-    if (const char *e = getenv("OSW_CHUNK_COLS")) { const int v = atoi(e); if (v >= 64) chunk_cols = (uint32_t)v; }   // experiments
+    if (c->tune.chunk_cols) chunk_cols = c->tune.chunk_cols;             // experiments
     if (max_chunk_residues && max_chunk_residues < chunk_cols) chunk_cols = (uint32_t)max_chunk_residues;
     const uint32_t n_shards = (uint32_t)shard_count * (uint32_t)c->n_dev;
     c->db_loaded = false;
@@ -429,10 +474,12 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
     if (want_all && (rc = grow_pinned(&d.h_scores, &d.h_scores_cap, (size_t)nq * (N ? N : 1))) != OSW_OK) return rc;
 
     const bool use_u16 = (c->kernel_mask & OSW_K_U16) != 0;
+    d.h_counts[0] = 0;                 // an empty shard launches nothing: its flagged count must not be a previous search's
     uint32_t flag_cap = 0;
     if (use_u16) {
         uint64_t want = std::max<uint64_t>(FLAG_CAPACITY_MIN, (uint64_t)nq * N / 64);
         flag_cap = (uint32_t)std::min<uint64_t>(want, 1u << 26);
+        if (c->tune.flag_cap) flag_cap = c->tune.flag_cap;             // tests: force several re-score rounds
         size_t cap = d.pairs_cap;
         if ((rc = grow(&d.d_pairs, &cap, flag_cap)) != OSW_OK) return rc;
         d.pairs_cap = (uint32_t)cap;
@@ -443,8 +490,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             // The bottom rows take 8 bytes per column - 8 x the database itself.  They are kept for one
             // SEGMENT of consecutive chunks at a time (all passes run over a segment before the next
             // one starts), so the buffer is bounded whatever the database size.
-            size_t budget_cols = (size_t)2 << 30;            // 16 GiB
-            if (const char *e = getenv("OSW_BOUND_BUDGET_COLS")) { const long long v = atoll(e); if (v >= 1024) budget_cols = (size_t)v; }
+            const size_t budget_cols = c->tune.bound_budget_cols;            // 16 GiB unless a test shrinks it
             const size_t all_cols = std::max<uint64_t>(std::max<uint64_t>(s.stream_bytes, s.pair_cols), 1);
             const size_t want = std::min(all_cols, budget_cols + 2 * 65536 + 1024);
             const size_t had = d.bound_cap;
@@ -502,11 +548,10 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             // quarter of the scheduler's issue rate.  (Threshold 1.5 measured: at a ratio of 1.15 the
             // express CTAs cost 4 %, at 1.9 they gain 6 %, at 3.5 and above 20-40 %.)
             up.express_ctas = 0;
-            if (end > first && !getenv("OSW_NO_EXPRESS")) {
+            if (end > first && c->tune.express) {
                 const LaunchModel m(ps.G, ps.R, pd, (double)cols, d.n_sms);
                 const double longest = (double)chunk_cols(first);
-                double ratio = 1.5;
-                if (const char *e = getenv("OSW_EXPRESS_RATIO")) ratio = atof(e);        // experiments
+                const double ratio = c->tune.express_ratio;
                 if (longest * m.contended > ratio * m.t_pipe) {
                     const double cut = longest * m.alone / m.contended;      // shorter chunks finish in time anyway
                     uint32_t n = 0;
@@ -605,8 +650,7 @@ extern "C" int osw_search(osw_ctx *c, const uint8_t *queries, const uint32_t *q_
     // and, times the segments of a streamed database, MAX_LAUNCH_SLOTS).
     uint64_t n_max = 1;
     for (int i = 0; i < c->n_dev; ++i) n_max = std::max<uint64_t>(n_max, c->devs[i].shard.n_seqs);
-    uint64_t budget = (uint64_t)8 << 30;
-    if (const char *e = getenv("OSW_SCORE_BUDGET_KB")) { const long long v = atoll(e); if (v >= 1) budget = (uint64_t)v << 10; }
+    const uint64_t budget = c->tune.score_budget;
     const int batch = (int)std::max<uint64_t>(2, std::min<uint64_t>(std::min<uint64_t>((uint64_t)nq, 16384), budget / (4 * n_max)));
     const uint64_t max_rows = 1u << 20;
     osw_timing total;
@@ -642,7 +686,7 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
         for (int q = 0; q < nq; ++q) q_len[q] = q_off[q + 1] - q_off[q];
         passes.resize(MAX_PASSES);
         const int mode = (c->kernel_mask & OSW_K_PAIR_DB) ? OSW_PLAN_PAIR_DB : (c->kernel_mask & OSW_K_TWO_TRACK) ? OSW_PLAN_TWO_TRACK : OSW_PLAN_AUTO;
-        int n_pass = osw_plan_passes(q_len.data(), nq, passes.data(), MAX_PASSES, mode, 4);
+        int n_pass = osw_plan_passes_ex(q_len.data(), nq, passes.data(), MAX_PASSES, mode, 4, c->tune.rmax);
         if (n_pass < 0) { snprintf(g_err, sizeof g_err, "the queries need more than %d passes", MAX_PASSES); return OSW_E_ARG; }
         if (n_pass == 1 && passes[0].G < 32) {
             // The planner picked the geometry with the fewest padded rows.  That is the fastest one
@@ -661,11 +705,10 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
                 return std::max(m.t_pipe, t_chain) + 0.25 * std::min(m.t_pipe, t_chain);
             };
             double best = estimate(passes[0]);
-            int force_g = 0;
-            if (const char *e = getenv("OSW_MIN_G")) force_g = atoi(e);                 // experiments
+            const int force_g = c->tune.force_g;                 // experiments
             std::vector<OswPass> alt(2);
             for (int g = passes[0].G * 2; g <= 32; g *= 2) {
-                if (osw_plan_passes(q_len.data(), nq, alt.data(), 2, pd ? OSW_PLAN_PAIR_DB : OSW_PLAN_TWO_TRACK, g) != 1) continue;
+                if (osw_plan_passes_ex(q_len.data(), nq, alt.data(), 2, pd ? OSW_PLAN_PAIR_DB : OSW_PLAN_TWO_TRACK, g, c->tune.rmax) != 1) continue;
                 const double t = estimate(alt[0]);
                 if (force_g ? g == force_g : t < best) { best = t; passes[0] = alt[0]; }
             }
@@ -702,37 +745,49 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
             ip.scratch = d.d_scratch;
             return rc2;
         };
-        if (use_u16) {
-            // the flagged count was copied to h_counts in phase 1; wait for it (tiny sync per GPU)
+        if (use_u16 && N) {
+            // the flagged count was copied to h_counts in phase 1; wait for it (tiny sync per GPU).
+            // The list holds pairs_cap entries: when more pairs overflowed 16 bits, the listed ones
+            // are re-scored (which replaces their FLAGGED marker by the exact score) and the score
+            // matrix is scanned again for the rest - like the reference, which simply recomputes
+            // whatever saturated (HybridSearch.c:1032-1134), this never fails on data.
             CK(cudaStreamSynchronize(d.st));
             uint32_t n_flag = d.h_counts[0];
-            if (n_flag > d.pairs_cap) {
-                snprintf(g_err, sizeof g_err, "%u flagged pairs exceed the re-score list capacity %u", n_flag, d.pairs_cap);
-                return OSW_E_NOMEM;
-            }
-            rescored += n_flag;
-            if (n_flag) {
+            while (n_flag) {
+                const uint32_t n_now = std::min(n_flag, d.pairs_cap);
+                rescored += n_now;
                 int rc2 = need_scratch();
                 if (rc2 != OSW_OK) return rc2;
+                ip.stream = d.d_stream; ip.task_off = nullptr;
                 if (d.streaming) {
                     // the stream is not resident: gather the flagged sequences from the pinned host copy
-                    std::vector<uint2> hp(n_flag);
-                    CK(cudaMemcpy(hp.data(), d.d_pairs, (size_t)n_flag * sizeof(uint2), cudaMemcpyDeviceToHost));
-                    std::vector<uint64_t> off(n_flag);
+                    // into a pinned staging buffer and copy it in stream order
+                    if ((rc2 = grow_pinned(&d.h_pairs, &d.h_pairs_cap, (size_t)n_now)) != OSW_OK) return rc2;
+                    CK(cudaMemcpyAsync(d.h_pairs, d.d_pairs, (size_t)n_now * sizeof(uint2), cudaMemcpyDeviceToHost, d.st));
+                    CK(cudaStreamSynchronize(d.st));
+                    if ((rc2 = grow_pinned(&d.h_task_off, &d.h_task_off_cap, (size_t)n_now)) != OSW_OK) return rc2;
                     uint64_t total = 0;
-                    for (uint32_t k = 0; k < n_flag; ++k) { off[k] = total; total += s.seq_len[hp[k].y]; }
-                    std::vector<uint8_t> stage(total ? total : 1);
-                    for (uint32_t k = 0; k < n_flag; ++k)
-                        memcpy(stage.data() + off[k], d.h_stream + s.seq_off[hp[k].y], s.seq_len[hp[k].y]);
-                    if ((rc2 = grow(&d.d_stage, &d.stage_cap, stage.size())) != OSW_OK) return rc2;
-                    if ((rc2 = grow(&d.d_task_off, &d.task_off_cap, (size_t)n_flag)) != OSW_OK) return rc2;
-                    CK(cudaMemcpy(d.d_stage, stage.data(), stage.size(), cudaMemcpyHostToDevice));
-                    CK(cudaMemcpy(d.d_task_off, off.data(), (size_t)n_flag * sizeof(uint64_t), cudaMemcpyHostToDevice));
+                    for (uint32_t k = 0; k < n_now; ++k) { d.h_task_off[k] = total; total += s.seq_len[d.h_pairs[k].y]; }
+                    if ((rc2 = grow_pinned(&d.h_stage, &d.h_stage_cap, (size_t)(total ? total : 1))) != OSW_OK) return rc2;
+                    for (uint32_t k = 0; k < n_now; ++k)
+                        memcpy(d.h_stage + d.h_task_off[k], d.h_stream + s.seq_off[d.h_pairs[k].y], s.seq_len[d.h_pairs[k].y]);
+                    if ((rc2 = grow(&d.d_stage, &d.stage_cap, (size_t)(total ? total : 1))) != OSW_OK) return rc2;
+                    if ((rc2 = grow(&d.d_task_off, &d.task_off_cap, (size_t)n_now)) != OSW_OK) return rc2;
+                    CK(cudaMemcpyAsync(d.d_stage, d.h_stage, (size_t)total, cudaMemcpyHostToDevice, d.st));
+                    CK(cudaMemcpyAsync(d.d_task_off, d.h_task_off, (size_t)n_now * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st));
                     ip.stream = d.d_stage; ip.task_off = d.d_task_off;
                 }
-                ip.pairs = d.d_pairs; ip.n_tasks = n_flag;
-                osw_launch_i32(ip, (int)std::min<uint64_t>((uint64_t)i32_blocks, ((uint64_t)n_flag + 7) / 8), d.st);
+                ip.pairs = d.d_pairs; ip.n_tasks = n_now;
+                osw_launch_i32(ip, (int)std::min<uint64_t>((uint64_t)i32_blocks, ((uint64_t)n_now + 7) / 8), d.st);
                 ++launches;
+                if (n_flag <= d.pairs_cap) break;
+                // next round: scan for the pairs still flagged
+                CK(cudaMemsetAsync(d.d_counters, 0, sizeof(uint32_t), d.st));
+                CK(cudaMemsetAsync(d.d_task_counter, 0, 2 * sizeof(unsigned long long), d.st));
+                launches += osw_collect_flagged(d.d_scores, N, nq, d.d_pairs, d.d_counters, d.pairs_cap, d.st);
+                CK(cudaMemcpyAsync(d.h_counts, d.d_counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, d.st));
+                CK(cudaStreamSynchronize(d.st));
+                n_flag = d.h_counts[0];
             }
         } else if (N) {
             if (d.streaming) { snprintf(g_err, sizeof g_err, "the 32-bit-only mode needs a resident database"); return OSW_E_STATE; }
@@ -772,7 +827,7 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
         tm.rescore_ms = std::max(tm.rescore_ms, (double)ms_resc);
         tm.topr_ms = std::max(tm.topr_ms, (double)ms_top);
         if (i == 0) for (uint32_t k = 0; k < slots[i]; ++k) tm.sm_cycles += d.h_cycles[k];
-        if (i == 0 && getenv("OSW_TRACE")) {
+        if (i == 0 && c->tune.trace) {
             // per-launch report: geometry, elapsed SM cycles, padded cell updates per SM-cycle
             for (uint32_t k = 0; k < slots[i] && k < d.trace.size(); ++k) {
                 const LaunchRecord &lr = d.trace[k];

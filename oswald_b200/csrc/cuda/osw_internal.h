@@ -58,6 +58,8 @@ struct OswPass {
 #define OSW_PLAN_PAIR_DB 2
 // min_g: smallest group width allowed (4 = no restriction; 32 = one sequence per warp).
 extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes, int mode, int min_g);
+// rmax: rows per lane of the full-height passes (0 = default 40; experiments).
+int osw_plan_passes_ex(const uint32_t *q_len, int nq, OswPass *out, int max_passes, int mode, int min_g, int rmax);
 
 struct U16Params {
     const uint8_t   *stream;      // the columns [stream_col0, ...) of the shard's stream (all of it, or a window)

@@ -17,7 +17,7 @@ namespace {
 const int kG[4] = {4, 8, 16, 32};
 const int kNR = 10;
 const int kR[kNR] = {8, 12, 16, 20, 24, 28, 32, 36, 40, 44};
-int kRmax = 40;        // rows per lane of the full-height passes (OSW_RMAX overrides, for experiments)
+const int kRmaxDefault = 40;        // rows per lane of the full-height passes
 
 struct Track { std::vector<int> q; uint64_t rows = 0; };
 
@@ -60,11 +60,12 @@ int lanes_needed(const Track &tr, const uint32_t *q_len, size_t cur, uint32_t do
 static int pd_rmax(int G) { return G == 32 ? 28 : 40; }
 
 extern "C" int osw_plan_passes(const uint32_t *q_len, int nq, OswPass *out, int max_passes, int mode, int min_g) {
+    return osw_plan_passes_ex(q_len, nq, out, max_passes, mode, min_g, 0);
+}
+
+int osw_plan_passes_ex(const uint32_t *q_len, int nq, OswPass *out, int max_passes, int mode, int min_g, int rmax) {
     if (!q_len || nq < 1 || !out || max_passes < 1) return -1;
-    if (const char *e = getenv("OSW_RMAX")) {
-        const int v = atoi(e);
-        if (v >= 16 && v <= 44 && v % 4 == 0) kRmax = v;
-    }
+    const int kRmax = rmax >= 16 && rmax <= 44 && rmax % 4 == 0 ? rmax : kRmaxDefault;     // (experiments: OSW_RMAX)
     // longest first onto the lighter track (rows rounded up to whole lanes of the widest geometry)
     std::vector<int> order(nq);
     for (int i = 0; i < nq; ++i) order[i] = i;

@@ -95,6 +95,13 @@ void free_database(osw_database *db) {
     memset(db, 0, sizeof *db);
 }
 
+static const uint32_t *g_sort_indices;          /* (qsort has no context argument; the tool is single-threaded here) */
+static int cmp_request(const void *a, const void *b) {
+    const size_t x = *(const size_t *)a, y = *(const size_t *)b;
+    const uint32_t ix = g_sort_indices[x], iy = g_sort_indices[y];
+    return ix != iy ? (ix < iy ? -1 : 1) : (x < y ? -1 : x > y);
+}
+
 /* The reference loads all N titles (sequences.c:1096-1127); only the printed ones are needed:
  * one sequential scan of X.desc picks the requested lines. */
 int load_database_headers(const char *prefix, const uint32_t *indices, size_t n, char **result) {
@@ -102,14 +109,12 @@ int load_database_headers(const char *prefix, const uint32_t *indices, size_t n,
     snprintf(filename, sizeof filename, "%s.desc", prefix);
     FILE *f = fopen(filename, "r");
     if (!f) { printf("OSWALD: An error occurred while opening sequence description file.\n"); return 3; }
-    /* order the requests by index */
+    /* order the requests by index (n = nq * top: up to a few hundred thousand with many queries) */
     size_t *order = (size_t *)malloc((n ? n : 1) * sizeof(size_t));
+    if (!order) { fclose(f); printf("OSWALD: An error occurred while allocating memory.\n"); return 1; }
     for (size_t i = 0; i < n; ++i) order[i] = i;
-    for (size_t i = 1; i < n; ++i) {          /* insertion sort: n is nq*top, small */
-        size_t v = order[i], j = i;
-        while (j && indices[order[j - 1]] > indices[v]) { order[j] = order[j - 1]; --j; }
-        order[j] = v;
-    }
+    g_sort_indices = indices;
+    qsort(order, n, sizeof(size_t), cmp_request);
     for (size_t i = 0; i < n; ++i) result[i] = NULL;
     char *line = NULL; size_t cap = 0; ssize_t len;
     uint64_t lineno = 0; size_t k = 0;

@@ -166,6 +166,52 @@ def test_overflow_rescore_exact(searcher):
         assert tm["rescored_pairs"] == int((want + 9 + 1 + 1 + 32 >= 65504).sum())      # bias = go + 2*ge + 32
 
 
+def overflow_case(rng):
+    """Tryptophan-rich queries and sequences under PAM30 9/1: dozens of pairs beyond 16 bits."""
+    W = np.uint8(19)
+    qs = [AA[rng.integers(0, 20, size=120)], np.full(5300, W, dtype=np.uint8),
+          np.where(rng.random(5400) < 0.93, W, AA[rng.integers(0, 20, size=5400)]).astype(np.uint8)]
+    seqs = rand_seqs(rng, 300, 20, 300) + [np.full(int(n), W, dtype=np.uint8) for n in rng.integers(5100, 9000, size=24)]
+    return make_db(seqs), ob.Queries.from_list(qs)
+
+
+def test_rescore_in_rounds_when_the_flag_list_is_small(built, monkeypatch):
+    """More flagged pairs than the list holds: the 32-bit stage runs in rounds (re-score what is
+    listed, scan again) instead of failing - any input the reference accepts is accepted.  Also
+    with the database streamed through device windows (staged re-score)."""
+    monkeypatch.setenv("OSW_FLAG_CAP", "5")
+    rng = np.random.default_rng(66)
+    db, q = overflow_case(rng)
+    want = oracle_scores(q, db, "pam30", 9, 1)
+    n_over = int((want + 9 + 1 + 1 + 32 >= 65504).sum())
+    assert n_over > 3 * 5
+    for window in (0, 1 << 20):
+        with ob.Searcher(1) as s:
+            s.set_device_window(window)
+            s.load_db(db)
+            for mode in MODES.values():
+                tm = check(s, db, q, "pam30", 9, 1, 10, mask=mode, want=want)
+                assert tm["rescored_pairs"] == n_over
+
+
+def test_empty_shard_after_an_overflow_search(built):
+    """A context whose shard is empty (fewer chunks than shards) must not re-score from the flagged
+    count a previous search left behind."""
+    rng = np.random.default_rng(67)
+    db, q = overflow_case(rng)
+    tiny = make_db([AA[rng.integers(0, 20, size=50)]])
+    with ob.Searcher(1) as s:
+        s.load_db(db)
+        tm = check(s, db, q, "pam30", 9, 1, 10)
+        assert tm["rescored_pairs"] > 0
+        s.load_db(tiny, shard_rank=1, shard_count=4)            # one chunk, dealt to shard 0: this shard holds nothing
+        assert s.stats()["n_seqs"] == 0
+        hits, tm = s.search(q, ob.matrix("pam30"), 9, 1, top=10)
+        assert tm["rescored_pairs"] == 0 and all(h == [] for h in hits)
+        s.load_db(tiny)
+        check(s, tiny, q, "pam30", 9, 1, 10)
+
+
 def test_sharded_contexts_merge_to_the_same_hits(built):
     """Two shards (as two ranks would hold them) merged on the host == one unsharded search."""
     from oswald_b200.host import merge_hits
@@ -272,6 +318,13 @@ def test_invalid_inputs_are_rejected(searcher):
     bad_db = ob.Database(np.full(40, 30, dtype=np.uint8), np.array([0, 40], dtype=np.uint64))
     with pytest.raises(capi.OswError):
         searcher.load_db(bad_db)
+    # not in canonical (ascending length) order / offsets going backwards: rejected, not mis-scored
+    unsorted = ob.Database(AA[rng.integers(0, 20, size=60)], np.array([0, 40, 60], dtype=np.uint64))
+    with pytest.raises(capi.OswError):
+        searcher.load_db(unsorted)
+    backwards = ob.Database(AA[rng.integers(0, 20, size=60)], np.array([0, 40, 30, 60], dtype=np.uint64))
+    with pytest.raises(capi.OswError):
+        searcher.load_db(backwards)
     searcher.load_db(db)                       # the context stays usable
     check(searcher, db, q, "blosum62", 10, 2, 5)
 

@@ -1,5 +1,5 @@
 #!/bin/bash
-# End-of-round validation on one B200: smoke, GPU tests, bench (both arms), all five configs, the
+# End-of-round validation on one B200: smoke, GPU tests, bench (both arms; the bench carries all five configs), the
 # command-line tool at a moderate size, ncu evidence.   usage: bash tools/gpu_final.sh <tag>
 TAG=${1:-final}
 mkdir -p gpurun_out
@@ -13,7 +13,6 @@ d = json.load(open("gpurun_out/${TAG}_bench.json")); r = json.load(open("gpurun_
 print("ours %.1f GCUPS  e2e %.1f  frac %.3f  launches %d  clocks %s | reference %.1f GCUPS on %d cores" % (
     d["value"], d["e2e"]["value"], d["roofline"]["frac"], d["gpu_launches"], d["clocks"], r["value"], r["cpu_baseline"]["cores"]))
 PY
-timeout 2000 python tests/run_full_configs.py > gpurun_out/${TAG}_configs.jsonl 2> gpurun_out/${TAG}_configs.err; echo "configs rc=$?"; tail -1 gpurun_out/${TAG}_configs.jsonl
 # command-line tool: 100k sequences, 3 queries
 T=$(mktemp -d)
 ./tools/osw_synth db -n 100000 -mu 5.706 -sigma 0.6 -seed 5 -o $T/db.fasta

@@ -4,14 +4,14 @@
 # one full-size search.   usage (under gpurun): bash tools/gpu_profile.sh <tag>
 TAG=${1:-prof}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 0 --seqs-per-gpu 30000 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 0 --config 2 --seqs 30000 --no-cpu-baseline --no-extra --no-verify"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "launch list rc=$?"
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:sw_u16 -s 14 -c 2 -f -o gpurun_out/${TAG} $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "full capture rc=$?"
-FULL="python bench.py --steps 1 --warmup 0 --no-cpu-baseline"
+FULL="python bench.py --steps 1 --warmup 0 --config ${CFG:-3} --no-cpu-baseline --no-extra --no-verify"
 $FULL > gpurun_out/${TAG}_plain4.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_full.csv $FULL > gpurun_out/${TAG}_ncu4.log 2>&1
 echo "full-size launch list rc=$?"
@@ -19,5 +19,5 @@ $FULL > gpurun_out/${TAG}_plain3.log 2>&1 &&
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:sw_u16_kernel -c 17 --csv \
     --log-file gpurun_out/${TAG}_traffic.csv $FULL > gpurun_out/${TAG}_ncu3.log 2>&1
 echo "traffic capture rc=$?"
-python tools/ncu_traffic.py gpurun_out/${TAG}_traffic.csv gpurun_out/${TAG}_traffic.json "$FULL"
+python tools/ncu_traffic.py gpurun_out/${TAG}_traffic.csv gpurun_out/${TAG}_traffic.json "$FULL" ${CFG:-3}
 ls -la gpurun_out/
