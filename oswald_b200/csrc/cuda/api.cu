@@ -27,7 +27,7 @@ namespace {
 constexpr uint32_t MAX_LAUNCH_SLOTS = 4096;
 constexpr uint32_t FLAG_CAPACITY_MIN = 1u << 16;
 
-struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; uint32_t express; };
+struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; uint32_t express; uint32_t slot; };
 
 struct DevState {
     int dev = -1, n_sms = 0;
@@ -547,12 +547,16 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             // one warp per scheduler, so that they advance at the latency of a step rather than at a
             // quarter of the scheduler's issue rate.  (Threshold 1.5 measured: at a ratio of 1.15 the
             // express CTAs cost 4 %, at 1.9 they gain 6 %, at 3.5 and above 20-40 %.)
+            // When walking the longest chunk among three other busy warps would take clearly longer
+            // than the whole launch needs for its cell updates, the longest chunks get express CTAs:
+            // one warp per scheduler, so that they advance at the latency of a step rather than at a
+            // quarter of the scheduler's issue rate.  (Threshold 1.5 measured: at a ratio of 1.15 the
+            // express CTAs cost 4 %, at 1.9 they gain 6 %, at 3.5 and above 20-40 %.)
             up.express_ctas = 0;
             if (end > first && c->tune.express) {
                 const LaunchModel m(ps.G, ps.R, pd, (double)cols, d.n_sms);
                 const double longest = (double)chunk_cols(first);
-                const double ratio = c->tune.express_ratio;
-                if (longest * m.contended > ratio * m.t_pipe) {
+                if (longest * m.contended > c->tune.express_ratio * m.t_pipe) {
                     const double cut = longest * m.alone / m.contended;      // shorter chunks finish in time anyway
                     uint32_t n = 0;
                     while (first + n < end && n < 64u * m.groups && (double)chunk_cols(first + n) > cut) ++n;
@@ -568,7 +572,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             up.cycle_acc = d.d_cycles + slot;
             int rc2 = osw_launch_u16(up, ps, d.n_sms, d.st);
             if (rc2 != OSW_OK) { cuda_fail(cudaGetLastError(), "sw_u16 launch", __LINE__); return rc2; }
-            d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols, up.express_ctas});
+            d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols, up.express_ctas, slot});
             ++slot; *launches += 2;               // profile_build_kernel + sw_u16_kernel
             *padded_cells += (uint64_t)ps.G * ps.R * 2 * cols;
             return OSW_OK;
@@ -614,12 +618,47 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             }
         }
         CK(cudaEventRecord(d.ev[1], d.st));
-        *launches += osw_collect_flagged(d.d_scores, N, nq, d.d_pairs, d.d_counters, flag_cap, d.st);
-        CK(cudaMemcpyAsync(d.h_counts, d.d_counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, d.st));
     } else {
         CK(cudaEventRecord(d.ev[1], d.st));
     }
     *n_launch_slots = slot;
+    return OSW_OK;
+}
+
+// 32-bit kernel parameters for this GPU's shard.
+I32Params i32_params(const DevState &d, int go, int ge) {
+    const osw_shard &s = d.shard;
+    I32Params ip;
+    ip.stream = d.d_stream; ip.seq_off = d.d_seq_off; ip.seq_len = d.d_seq_len; ip.task_off = nullptr;
+    ip.queries = d.d_queries; ip.q_off = d.d_qoff; ip.matrix = d.d_matrix;
+    ip.pairs = nullptr; ip.n_tasks = 0; ip.n_tasks_dev = nullptr;
+    ip.n_seqs = s.n_seqs; ip.scores = d.d_scores; ip.scratch = d.d_scratch; ip.max_len = s.max_len ? s.max_len : 1;
+    ip.gap_open_extend = go + ge; ip.gap_extend = ge; ip.task_counter = d.d_task_counter;
+    return ip;
+}
+
+// Per-warp scratch of the 32-bit kernel (a pass's bottom row) for a grid of `blocks` blocks.
+int i32_scratch(DevState &d, int blocks) {
+    const size_t warps = (size_t)blocks * (osw_i32_block_threads() / 32);
+    return grow(&d.d_scratch, &d.scratch_cap, warps * (d.shard.max_len ? d.shard.max_len : 1));
+}
+
+// Top-r selection and the copies back to the host (keys, flagged count, cycle counters, all scores
+// on request), enqueued behind whatever has been enqueued on the GPU's stream.
+int enqueue_finish(osw_ctx *c, DevState &d, int nq, uint32_t top_r, bool want_all, bool list_flags, uint32_t slots,
+                   cudaEvent_t ev_before, cudaEvent_t ev_after, uint64_t *launches) {
+    const uint64_t N = d.shard.n_seqs;
+    CK(cudaEventRecord(ev_before, d.st));
+    const uint32_t r = (uint32_t)std::min<uint64_t>((uint64_t)top_r, N);
+    // the first scan of the selection also lists the pairs the 16-bit stage flagged (d_counters[0] counts them)
+    const FlagList fl = {d.d_pairs, d.d_counters, d.pairs_cap};
+    if (N) *launches += osw_topr_select(d.d_scores, d.d_canon, N, std::max<uint64_t>(c->n_seqs_canon, 1), nq, r, d.topr, list_flags ? &fl : nullptr, d.st);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev_after, d.st));
+    if (list_flags) CK(cudaMemcpyAsync(d.h_counts, d.d_counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, d.st));
+    if (r) CK(cudaMemcpyAsync(d.h_keys, d.topr.out_keys, (size_t)nq * r * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.st));
+    if (want_all && N) CK(cudaMemcpyAsync(d.h_scores, d.d_scores, (size_t)nq * N * sizeof(int32_t), cudaMemcpyDeviceToHost, d.st));
+    if (slots) CK(cudaMemcpyAsync(d.h_cycles, d.d_cycles, slots * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.st));
     return OSW_OK;
 }
 
@@ -726,42 +765,66 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
         if (rc != OSW_OK) return rc;
     }
     const double t_h2d = now_ms();
-    // ---- phase 2: re-score (needs the flagged count to size nothing - only to report it) ---
+    // ---- phase 2: top-r, enqueued WITHOUT waiting for the first stage --------------------------
+    // The first scan of the selection also lists the pairs whose 16-bit score may have wrapped.
+    // Nearly every search has none, and then it was one uninterrupted sequence of launches per GPU
+    // (a host round trip between scoring and top-r cost 15-40 ms per search under torchrun); when
+    // there are some, the selection is void: phase 3 re-scores them at 32 bit and selects again.
+    const int i32_blocks_rescore = 2, i32_blocks_all = 8;          // blocks per SM
+    for (int i = 0; i < c->n_dev; ++i) {
+        DevState &d = c->devs[i];
+        const uint64_t N = d.shard.n_seqs;
+        CK(cudaSetDevice(d.dev));
+        if (!use_u16 && N) {
+            if (d.streaming) { snprintf(g_err, sizeof g_err, "the 32-bit-only mode needs a resident database"); return OSW_E_STATE; }
+            int rc2 = i32_scratch(d, d.n_sms * i32_blocks_all);
+            if (rc2 != OSW_OK) return rc2;
+            I32Params ip = i32_params(d, go, ge);
+            ip.n_tasks = (uint64_t)nq * N;
+            rescored += ip.n_tasks;
+            osw_launch_i32(ip, d.n_sms * i32_blocks_all, d.st);
+            ++launches;
+        }
+        CK(cudaGetLastError());
+        int rc2 = enqueue_finish(c, d, nq, (uint32_t)top_r, all_scores != nullptr, use_u16, slots[i], d.ev[2], d.ev[3], &launches);
+        if (rc2 != OSW_OK) return rc2;
+    }
+    // ---- phase 3: wait; rare slow paths; order, merge ------------------------------------------
+    osw_timing tm;
+    memset(&tm, 0, sizeof tm);
+    std::vector<std::vector<osw_hit>> per_dev((size_t)c->n_dev);
     for (int i = 0; i < c->n_dev; ++i) {
         DevState &d = c->devs[i];
         const osw_shard &s = d.shard;
         const uint64_t N = s.n_seqs;
         CK(cudaSetDevice(d.dev));
-        I32Params ip;
-        ip.stream = d.d_stream; ip.seq_off = d.d_seq_off; ip.seq_len = d.d_seq_len; ip.task_off = nullptr;
-        ip.queries = d.d_queries; ip.q_off = d.d_qoff; ip.matrix = d.d_matrix;
-        ip.n_seqs = N; ip.scores = d.d_scores; ip.scratch = d.d_scratch; ip.max_len = s.max_len ? s.max_len : 1;
-        ip.gap_open_extend = go + ge; ip.gap_extend = ge; ip.task_counter = d.d_task_counter;
-        const int i32_blocks = d.n_sms * 4;
-        // per-warp scratch of the 32-bit kernel (a pass's bottom row): allocated when first needed
-        auto need_scratch = [&]() -> int {
-            const size_t warps = (size_t)i32_blocks * (osw_i32_block_threads() / 32);
-            int rc2 = grow(&d.d_scratch, &d.scratch_cap, warps * (s.max_len ? s.max_len : 1));
-            ip.scratch = d.d_scratch;
-            return rc2;
-        };
-        if (use_u16 && N) {
-            // the flagged count was copied to h_counts in phase 1; wait for it (tiny sync per GPU).
-            // The list holds pairs_cap entries: when more pairs overflowed 16 bits, the listed ones
-            // are re-scored (which replaces their FLAGGED marker by the exact score) and the score
-            // matrix is scanned again for the rest - like the reference, which simply recomputes
-            // whatever saturated (HybridSearch.c:1032-1134), this never fails on data.
-            CK(cudaStreamSynchronize(d.st));
-            uint32_t n_flag = d.h_counts[0];
-            while (n_flag) {
+        CK(cudaStreamSynchronize(d.st));
+        cudaEvent_t ev_end = d.ev[3];
+        uint32_t n_flag = use_u16 && N ? d.h_counts[0] : 0u;
+        // The 32-bit stage (rare): re-score the listed pairs - which replaces their FLAGGED marker by
+        // the exact score - and, when more pairs were flagged than the list holds, scan the score
+        // matrix for the rest and repeat: like the reference, which simply recomputes whatever
+        // saturated (HybridSearch.c:1032-1134), this never fails on data.  With a streamed database
+        // the flagged sequences are gathered from the pinned host copy into a staging buffer.  Then
+        // the selection is done again.
+        if (n_flag) {
+            bool listed = true;               // d_pairs holds min(n_flag, capacity) pairs still to be re-scored
+            for (;;) {
+                if (!listed) {
+                    CK(cudaMemsetAsync(d.d_counters, 0, sizeof(uint32_t), d.st));
+                    launches += osw_collect_flagged(d.d_scores, N, nq, d.d_pairs, d.d_counters, d.pairs_cap, d.st);
+                    CK(cudaMemcpyAsync(d.h_counts, d.d_counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, d.st));
+                    CK(cudaStreamSynchronize(d.st));
+                    n_flag = d.h_counts[0];
+                    if (!n_flag) break;
+                }
+                listed = false;
                 const uint32_t n_now = std::min(n_flag, d.pairs_cap);
                 rescored += n_now;
-                int rc2 = need_scratch();
+                int rc2 = i32_scratch(d, d.n_sms * i32_blocks_rescore);
                 if (rc2 != OSW_OK) return rc2;
-                ip.stream = d.d_stream; ip.task_off = nullptr;
+                I32Params ip = i32_params(d, go, ge);
                 if (d.streaming) {
-                    // the stream is not resident: gather the flagged sequences from the pinned host copy
-                    // into a pinned staging buffer and copy it in stream order
                     if ((rc2 = grow_pinned(&d.h_pairs, &d.h_pairs_cap, (size_t)n_now)) != OSW_OK) return rc2;
                     CK(cudaMemcpyAsync(d.h_pairs, d.d_pairs, (size_t)n_now * sizeof(uint2), cudaMemcpyDeviceToHost, d.st));
                     CK(cudaStreamSynchronize(d.st));
@@ -778,50 +841,27 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
                     ip.stream = d.d_stage; ip.task_off = d.d_task_off;
                 }
                 ip.pairs = d.d_pairs; ip.n_tasks = n_now;
-                osw_launch_i32(ip, (int)std::min<uint64_t>((uint64_t)i32_blocks, ((uint64_t)n_now + 7) / 8), d.st);
-                ++launches;
-                if (n_flag <= d.pairs_cap) break;
-                // next round: scan for the pairs still flagged
-                CK(cudaMemsetAsync(d.d_counters, 0, sizeof(uint32_t), d.st));
                 CK(cudaMemsetAsync(d.d_task_counter, 0, 2 * sizeof(unsigned long long), d.st));
-                launches += osw_collect_flagged(d.d_scores, N, nq, d.d_pairs, d.d_counters, d.pairs_cap, d.st);
-                CK(cudaMemcpyAsync(d.h_counts, d.d_counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, d.st));
-                CK(cudaStreamSynchronize(d.st));
-                n_flag = d.h_counts[0];
+                osw_launch_i32(ip, (int)std::min<uint64_t>((uint64_t)d.n_sms * i32_blocks_rescore, ((uint64_t)n_now + 3) / 4), d.st);
+                ++launches;
+                CK(cudaGetLastError());
+                if (n_flag <= d.pairs_cap) break;
             }
-        } else if (N) {
-            if (d.streaming) { snprintf(g_err, sizeof g_err, "the 32-bit-only mode needs a resident database"); return OSW_E_STATE; }
-            int rc2 = need_scratch();
+            int rc2 = enqueue_finish(c, d, nq, (uint32_t)top_r, all_scores != nullptr, false, slots[i], d.ev[4], d.ev[5], &launches);
             if (rc2 != OSW_OK) return rc2;
-            ip.pairs = nullptr; ip.n_tasks = (uint64_t)nq * N;
-            rescored += ip.n_tasks;
-            osw_launch_i32(ip, i32_blocks, d.st);
-            ++launches;
+            CK(cudaStreamSynchronize(d.st));
+            ev_end = d.ev[5];
         }
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(d.ev[2], d.st));
-        const uint32_t r = (uint32_t)std::min<uint64_t>((uint64_t)top_r, N);
-        if (r) launches += osw_topr_select(d.d_scores, d.d_canon, N, std::max<uint64_t>(c->n_seqs_canon, 1), nq, r, d.topr, d.st);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(d.ev[3], d.st));
-        if (r) CK(cudaMemcpyAsync(d.h_keys, d.topr.out_keys, (size_t)nq * r * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.st));
-        if (all_scores && N) CK(cudaMemcpyAsync(d.h_scores, d.d_scores, (size_t)nq * N * sizeof(int32_t), cudaMemcpyDeviceToHost, d.st));
-        if (slots[i]) CK(cudaMemcpyAsync(d.h_cycles, d.d_cycles, slots[i] * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.st));
-    }
-    // ---- phase 3: wait, order, merge ---------------------------------------------------------
-    osw_timing tm;
-    memset(&tm, 0, sizeof tm);
-    std::vector<std::vector<osw_hit>> per_dev((size_t)c->n_dev);
-    for (int i = 0; i < c->n_dev; ++i) {
-        DevState &d = c->devs[i];
-        const uint64_t N = d.shard.n_seqs;
-        CK(cudaSetDevice(d.dev));
-        CK(cudaStreamSynchronize(d.st));
         float ms_total = 0, ms_score = 0, ms_resc = 0, ms_top = 0;
-        CK(cudaEventElapsedTime(&ms_total, d.ev[0], d.ev[3]));
+        CK(cudaEventElapsedTime(&ms_total, d.ev[0], ev_end));
         CK(cudaEventElapsedTime(&ms_score, d.ev[0], d.ev[1]));
         CK(cudaEventElapsedTime(&ms_resc, d.ev[1], d.ev[2]));
         CK(cudaEventElapsedTime(&ms_top, d.ev[2], d.ev[3]));
+        if (ev_end != d.ev[3]) {                 // slow path: everything after the first top-r counts as re-score
+            float ms_extra = 0;
+            CK(cudaEventElapsedTime(&ms_extra, d.ev[3], ev_end));
+            ms_resc += ms_extra;
+        }
         tm.device_ms = std::max(tm.device_ms, (double)ms_total);
         tm.score_ms = std::max(tm.score_ms, (double)ms_score);
         tm.rescore_ms = std::max(tm.rescore_ms, (double)ms_resc);
@@ -829,12 +869,13 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
         if (i == 0) for (uint32_t k = 0; k < slots[i]; ++k) tm.sm_cycles += d.h_cycles[k];
         if (i == 0 && c->tune.trace) {
             // per-launch report: geometry, elapsed SM cycles, padded cell updates per SM-cycle
-            for (uint32_t k = 0; k < slots[i] && k < d.trace.size(); ++k) {
+            for (uint32_t k = 0; k < d.trace.size(); ++k) {
                 const LaunchRecord &lr = d.trace[k];
+                const unsigned long long cyc = std::max<unsigned long long>(d.h_cycles[lr.slot], 1);
                 const double cells = 2.0 * lr.G * lr.R * (double)lr.cols;
                 fprintf(stderr, "osw trace: launch %u/%zu G=%d R=%d in=%d out=%d pairdb=%d express=%u chunks [%u,%u)  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
                         k + 1, d.trace.size(), lr.G, lr.R, lr.has_in, lr.has_out, lr.pair_db, lr.express, lr.first, lr.end,
-                        (unsigned long long)(d.h_cycles[k] / d.n_sms), cells / (double)d.h_cycles[k]);
+                        cyc / d.n_sms, cells / (double)cyc);
             }
         }
         const uint32_t r = (uint32_t)std::min<uint64_t>((uint64_t)top_r, N);

@@ -18,7 +18,9 @@ struct I32Params {
     const int8_t   *matrix;      // [24*32]
     const uint2    *pairs;       // (query, local sequence) list, or nullptr = all pairs
     const uint64_t *task_off;    // optional: stream offset of each task's sequence (replaces seq_off[s]; staged re-score)
-    uint64_t        n_tasks;     // pairs in the list, or nq*n_seqs
+    uint64_t        n_tasks;     // pairs in the list (an upper bound when n_tasks_dev is set), or nq*n_seqs
+    const uint32_t *n_tasks_dev; // optional: the list's length, read on the device (min with n_tasks) - lets the
+                                 // re-score be enqueued before the host knows how many pairs the first stage flagged
     uint64_t        n_seqs;
     int32_t        *scores;      // [nq][n_seqs]
     int2           *scratch;     // [warps_in_grid][max_len] (H,F) of a pass's bottom row
@@ -94,10 +96,15 @@ struct TopRWork {            // per-device scratch, sized for nq_max queries
     uint32_t *out_count;     // [nq]
     unsigned long long *out_keys;  // [nq][r]
 };
+#define OSW_TOPR_SMALL_MAX 24576      // sequences per shard up to which top-r is one launch (keys in shared memory)
 // Selects for each of nq rows the top_r largest keys (score<<32 | canonical index) into
 // w.out_keys (unordered).  Returns number of kernels launched.
+// flags (optional): the first scan over the scores also lists every (query, local sequence) whose
+// score is OSW_SCORE_FLAGGED - up to flags->capacity pairs, *flags->count counts all of them.  When
+// that count comes back non-zero the selection is void: the caller re-scores the pairs and selects again.
+struct FlagList { uint2 *pairs; uint32_t *count; uint32_t capacity; };
 int osw_topr_select(const int32_t *scores, const uint32_t *canon, uint64_t n_seqs, uint64_t n_canon, int nq,
-                    uint32_t top_r, const TopRWork &w, cudaStream_t st);
+                    uint32_t top_r, const TopRWork &w, const FlagList *flags, cudaStream_t st);
 // Marks flagged scores: appends (q, seq) of every score == OSW_SCORE_FLAGGED to pairs.
 int osw_collect_flagged(const int32_t *scores, uint64_t n_seqs, int nq, uint2 *pairs,
                         uint32_t *count, uint32_t capacity, cudaStream_t st);

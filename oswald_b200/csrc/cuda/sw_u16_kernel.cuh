@@ -553,4 +553,7 @@ int launch_g16(int R, const KArgs &a, int n_sms, cudaStream_t st);
 int launch_g32(int R, const KArgs &a, int n_sms, cudaStream_t st);
 
 }  // namespace osw_u16
+
+// bias, gap words and lane descriptors of a launch (sw_u16.cu)
+void osw_fill_kargs(osw_u16::KArgs &a, const U16Params &p, const OswPass &pass);
 #endif

@@ -20,6 +20,11 @@ __device__ __forceinline__ unsigned long long make_key(int score, uint32_t canon
     return ((unsigned long long)(uint32_t)score << 32) | canon;    // scores are >= 0
 }
 
+__device__ __forceinline__ void list_flagged(const FlagList &fl, uint32_t q, uint32_t i) {
+    const uint32_t slot = atomicAdd(fl.count, 1u);
+    if (slot < fl.capacity) fl.pairs[slot] = make_uint2(q, i);
+}
+
 // Round j's pick, by a whole block of 256 threads: the digit whose bin holds the need-th largest
 // key among those matching the prefix.  Returns prefix | digit << shift and the rank left inside
 // that bin.  sh: 256 words of shared memory.
@@ -58,7 +63,7 @@ __device__ __forceinline__ void state_before_round(const Rounds &rd, int j, int 
 
 // round j: count byte values among the keys whose higher (examined) bytes equal the prefix's
 __global__ void __launch_bounds__(THREADS)
-topr_round_kernel(const int32_t *scores, const uint32_t *canon, uint64_t n, uint32_t r, int j, Rounds rd, TopRWork w) {
+topr_round_kernel(const int32_t *scores, const uint32_t *canon, uint64_t n, uint32_t r, int j, Rounds rd, TopRWork w, FlagList fl) {
     __shared__ uint32_t sh[256];
     const int q = blockIdx.y;
     unsigned long long pre; uint32_t need;
@@ -69,7 +74,9 @@ topr_round_kernel(const int32_t *scores, const uint32_t *canon, uint64_t n, uint
     const unsigned long long himask = j ? ~0ull << (rd.shift[j - 1]) : 0ull;      // the bytes examined so far (skipped ones are 0 in every key)
     const int32_t *row = scores + (size_t)q * n;
     for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * THREADS) {
-        unsigned long long k = make_key(row[i], canon[i]);
+        const int sc = row[i];
+        if (sc == OSW_SCORE_FLAGGED && fl.count) list_flagged(fl, (uint32_t)q, (uint32_t)i);      // (first round only)
+        unsigned long long k = make_key(sc, canon[i]);
         if ((k & himask) == pre) atomicAdd(&sh[(k >> shift) & 255], 1u);
     }
     __syncthreads();
@@ -88,6 +95,66 @@ topr_gather_kernel(const int32_t *scores, const uint32_t *canon, uint64_t n, uin
         unsigned long long k = make_key(row[i], canon[i]);
         if (k >= thr) {
             uint32_t slot = atomicAdd(&w.out_count[q], 1u);
+            if (slot < r) w.out_keys[(size_t)q * r + slot] = k;
+        }
+    }
+}
+
+// Small databases (n <= TOPR_SMALL_MAX): the whole selection in ONE launch, one CTA per query.  The
+// keys are read from global memory once, into shared memory; the radix rounds and the final gather
+// work there (a tiny search is bound by launch count, not by the scan: 7 launches -> 1).
+constexpr int SMALL_THREADS = 512;
+__global__ void __launch_bounds__(SMALL_THREADS)
+topr_small_kernel(const int32_t *scores, const uint32_t *canon, uint32_t n, uint32_t r, Rounds rd, TopRWork w, FlagList fl) {
+    extern __shared__ __align__(16) unsigned long long s_keys[];     // [n]
+    __shared__ uint32_t hist[256], suffix[256];
+    __shared__ unsigned long long s_pre;
+    __shared__ uint32_t s_need, s_count;
+    const int q = blockIdx.x;
+    const int32_t *row = scores + (size_t)q * n;
+    for (uint32_t i = threadIdx.x; i < n; i += SMALL_THREADS) {
+        const int sc = row[i];
+        if (sc == OSW_SCORE_FLAGGED && fl.count) list_flagged(fl, (uint32_t)q, i);
+        s_keys[i] = make_key(sc, canon[i]);
+    }
+    if (threadIdx.x == 0) { s_pre = 0; s_need = r; s_count = 0; }
+    __syncthreads();
+    for (int j = 0; j < rd.n; ++j) {
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const int shift = rd.shift[j];
+        const unsigned long long himask = j ? ~0ull << (rd.shift[j - 1]) : 0ull, pre = s_pre;
+        const uint32_t need = s_need;
+        for (uint32_t i = threadIdx.x; i < n; i += SMALL_THREADS) {
+            const unsigned long long k = s_keys[i];
+            if ((k & himask) == pre) atomicAdd(&hist[(k >> shift) & 255], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {          // one warp: suffix sums over the 256 bins (8 per lane), then the pick
+            uint32_t loc[8], sum = 0;
+#pragma unroll
+            for (int k = 7; k >= 0; --k) { sum += hist[threadIdx.x * 8 + k]; loc[k] = sum; }
+            uint32_t above = 0;          // keys in the bins of higher lanes
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_down_sync(0xffffffffu, sum, o);
+                if ((int)threadIdx.x + o < 32) sum += v;
+            }
+            above = sum - loc[0];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) suffix[threadIdx.x * 8 + k] = loc[k] + above;
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            const uint32_t at = suffix[threadIdx.x], above = threadIdx.x < 255 ? suffix[threadIdx.x + 1] : 0u;
+            if (at >= need && above < need) { s_pre = pre | ((unsigned long long)threadIdx.x << shift); s_need = need - above; }
+        }
+        __syncthreads();
+    }
+    const unsigned long long thr = s_pre;       // the r-th largest key itself
+    for (uint32_t i = threadIdx.x; i < n; i += SMALL_THREADS) {
+        const unsigned long long k = s_keys[i];
+        if (k >= thr) {
+            const uint32_t slot = atomicAdd(&s_count, 1u);
             if (slot < r) w.out_keys[(size_t)q * r + slot] = k;
         }
     }
@@ -115,20 +182,35 @@ int grid_x(uint64_t n) {
 }  // namespace
 
 int osw_topr_select(const int32_t *scores, const uint32_t *canon, uint64_t n_seqs, uint64_t n_canon, int nq,
-                    uint32_t top_r, const TopRWork &w, cudaStream_t st) {
+                    uint32_t top_r, const TopRWork &w, const FlagList *flags, cudaStream_t st) {
     uint32_t r = top_r < n_seqs ? top_r : (uint32_t)n_seqs;
-    if (r == 0) return 0;
+    const FlagList none = {nullptr, nullptr, 0};
+    if (r == 0) {          // nothing to select: the flagged pairs still have to be found
+        if (flags && n_seqs) return osw_collect_flagged(scores, n_seqs, nq, flags->pairs, flags->count, flags->capacity, st);
+        return 0;
+    }
     Rounds rd;
     rd.n = 0;
     for (int byte = 6; byte >= 0; --byte) {          // byte 7 = score bits 24-31: never set
         if (byte < 4 && byte > 0 && ((n_canon - 1) >> (8 * byte)) == 0) continue;     // index bytes above the database size
         rd.shift[rd.n++] = 8 * byte;
     }
+    if (n_seqs <= OSW_TOPR_SMALL_MAX) {
+        static bool configured[64] = {};          // the attribute is per device; set once (idempotent, so a race is harmless)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
+            cudaFuncSetAttribute(topr_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OSW_TOPR_SMALL_MAX * 8);
+            if (dev >= 0 && dev < 64) configured[dev] = true;
+        }
+        topr_small_kernel<<<nq, SMALL_THREADS, (size_t)n_seqs * 8, st>>>(scores, canon, (uint32_t)n_seqs, r, rd, w, flags ? *flags : none);
+        return 1;
+    }
     cudaMemsetAsync(w.hist, 0, (size_t)nq * 8 * 256 * sizeof(uint32_t), st);
     cudaMemsetAsync(w.out_count, 0, (size_t)nq * sizeof(uint32_t), st);
     dim3 grid(grid_x(n_seqs), nq);
     for (int j = 0; j < rd.n; ++j)
-        topr_round_kernel<<<grid, THREADS, 0, st>>>(scores, canon, n_seqs, r, j, rd, w);
+        topr_round_kernel<<<grid, THREADS, 0, st>>>(scores, canon, n_seqs, r, j, rd, w, j == 0 && flags ? *flags : none);
     topr_gather_kernel<<<grid, THREADS, 0, st>>>(scores, canon, n_seqs, r, rd, w);
     return rd.n + 1;
 }
