@@ -140,7 +140,8 @@ size_t osw_merge_hits(const osw_hit *const *lists, const uint32_t *counts, int n
 int osw_calibrate(int device, double out[12]);
 /* Co-issue probe: for 12 instruction classes (VIADDMNMX.U16x2, VIMNMX3.U16x2, VIADD, IMAD, HMNMX2,
  * VIMNMX.U16x2, VIMNMX.U32, LOP3, FMNMX, PRMT, SHF, HADD2) out[3k..3k+2] = thread instructions per
- * SM-cycle of the class alone, of 8 VIADDMNMX + 8 of it, of 8 VIADDMNMX + 4 of it.  n_out >= 36. */
+ * SM-cycle of the class alone, of 8 VIADDMNMX + 8 of it, of 8 VIADDMNMX + 4 of it.  n_out >= 36; with
+ * n_out >= 45 three more classes follow (IMAD.HI, LEA.HI, IMAD by a run-time 65536). */
 int osw_calibrate_mix(int device, double *out, int n_out);
 
 /* ---- substitution matrices: the reference's eight tables (submat.c:4-227), selected by the

@@ -184,7 +184,7 @@ extern "C" int osw_calibrate(int device, double out[12]) {
 namespace {
 
 enum { OP_NONE = -1, OP_VIADDMNMX = 0, OP_VIMNMX3, OP_VIADD, OP_IMAD, OP_HMNMX2, OP_VIMNMX2, OP_IMNMX, OP_LOP3,
-       OP_FMNMX, OP_PRMT, OP_SHF, OP_HADD2, OP_COUNT };
+       OP_FMNMX, OP_PRMT, OP_SHF, OP_HADD2, OP_COUNT, OP_IMADHI = OP_COUNT, OP_LEAHI, OP_IMADSHL, OP_COUNT_EXT };
 
 template <int OP>
 __device__ __forceinline__ uint32_t apply(uint32_t x, uint32_t a, uint32_t b) {
@@ -201,6 +201,9 @@ __device__ __forceinline__ uint32_t apply(uint32_t x, uint32_t a, uint32_t b) {
     else if (OP == OP_PRMT) asm volatile("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(r) : "r"(x), "r"(a));
     else if (OP == OP_SHF) asm volatile("shf.l.wrap.b32 %0, %1, %2, 3;" : "=r"(r) : "r"(x), "r"(a));
     else if (OP == OP_HADD2) asm volatile("add.f16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(a));
+    else if (OP == OP_IMADHI) asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(a), "r"(b));      // (x * a >> 32) + b
+    else if (OP == OP_LEAHI) r = (x >> 16) + a;                      // LEA.HI: the high half moved down, plus a word
+    else if (OP == OP_IMADSHL) asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(b), "r"(a));     // x * b + a, b = 65536 at run time
     return r;
 }
 
@@ -269,6 +272,12 @@ extern "C" int osw_calibrate_mix(int device, double *out, int n_out) {
     probe_pair<OP_PRMT>(n_sms, g, out + 27, out + 28, out + 29);
     probe_pair<OP_SHF>(n_sms, g, out + 30, out + 31, out + 32);
     probe_pair<OP_HADD2>(n_sms, g, out + 33, out + 34, out + 35);
+    if (n_out >= 3 * OP_COUNT_EXT) {          // the unpack candidates of the 16-bit pair-database tables
+        g.b = 0x00010000u;
+        probe_pair<OP_IMADHI>(n_sms, g, out + 36, out + 37, out + 38);
+        probe_pair<OP_LEAHI>(n_sms, g, out + 39, out + 40, out + 41);
+        probe_pair<OP_IMADSHL>(n_sms, g, out + 42, out + 43, out + 44);
+    }
     cudaFree(g.cycles); cudaFree(g.sink);
     return cudaDeviceSynchronize() == cudaSuccess ? OSW_OK : OSW_E_CUDA;
 }

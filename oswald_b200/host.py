@@ -234,12 +234,12 @@ def calibrate(device=0):
 
 
 MIX_CLASSES = ["VIADDMNMX.U16x2", "VIMNMX3.U16x2", "VIADD", "IMAD", "HMNMX2", "VIMNMX.U16x2", "VIMNMX.U32", "LOP3",
-               "FMNMX", "PRMT", "SHF", "HADD2"]
+               "FMNMX", "PRMT", "SHF", "HADD2", "IMAD.HI", "LEA.HI", "IMAD(x65536)"]
 
 
 def calibrate_mix(device=0):
     """Issue rates (thread instructions per SM-cycle): alone / with 8 DPX + 8 / with 8 DPX + 4."""
-    out = (C.c_double * 36)()
-    capi.check(capi.lib().osw_calibrate_mix(device, out, 36), "osw_calibrate_mix")
+    out = (C.c_double * 45)()
+    capi.check(capi.lib().osw_calibrate_mix(device, out, 45), "osw_calibrate_mix")
     return {name: {"alone": out[3 * k], "dpx8_plus8_total": out[3 * k + 1], "dpx8_plus4_total": out[3 * k + 2]}
             for k, name in enumerate(MIX_CLASSES)}

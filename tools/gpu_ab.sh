@@ -12,15 +12,16 @@ run() {
   for rep in 1 2; do
     for V in new base; do
       if [ $V = base ]; then PRE="env $BASE"; else PRE="env"; fi
-      OSW_TRACE=1 timeout 300 $PRE python bench.py --no-cpu-baseline "$@" 2> gpurun_out/${TAG}.err | python -c "
+      OSW_TRACE=1 timeout 300 $PRE python bench.py --no-cpu-baseline --no-extra --no-verify "$@" 2> gpurun_out/${TAG}.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('$label $V: %.1f GCUPS  e2e %.1f  score %.3f ms  busy-clk %.2f' % (d['value'], d['e2e']['value'], d['breakdown_ms']['score'], d['roofline']['achieved_cells_per_busy_sm_clk']))"
     done
   done
 }
 if [ $# -gt 0 ]; then run custom "$@"; exit 0; fi
-run c2 --steps 3 --warmup 2
-run q5478 --steps 2 --warmup 1 --query-lengths 5478
-run q144 --steps 2 --warmup 1 --query-lengths 144
-run c1 --steps 5 --warmup 3 --seqs-per-gpu 10000 --query-lengths 144
-run s100k --steps 3 --warmup 2 --seqs-per-gpu 100000 --query-lengths 144
+run c2 --config 2 --steps 3 --warmup 2
+run q5478 --config 2 --steps 2 --warmup 1 --query-lengths 5478
+run q144 --config 2 --steps 2 --warmup 1 --query-lengths 144
+run q1000 --config 2 --steps 2 --warmup 1 --query-lengths 1000
+run c1 --config 1 --steps 10 --warmup 3
+run s100k --config 2 --steps 3 --warmup 2 --seqs 100000 --query-lengths 144
