@@ -38,7 +38,9 @@ enum {
     OSW_E_CUDA = -3,       /* a CUDA runtime call failed (osw_last_error has the text) */
     OSW_E_NOMEM = -4,      /* host or device allocation failed */
     OSW_E_STATE = -5,      /* call order wrong (e.g. search before db_load) */
-    OSW_E_ARCH = -6        /* device is not sm_100 */
+    OSW_E_ARCH = -6,       /* device is not sm_100 */
+    OSW_E_IO = -7,         /* a file cannot be opened / written */
+    OSW_E_FORMAT = -8      /* not an X.osw file of this format version, or truncated / corrupt */
 };
 
 typedef struct osw_ctx osw_ctx;
@@ -95,6 +97,23 @@ void osw_free(osw_ctx *ctx);
  * -k (arguments.c:113-117); 0 = default. */
 int osw_db_load(osw_ctx *ctx, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
                 int shard_rank, int shard_count, uint64_t max_chunk_residues);
+/* ---- the preprocessed database in its device layout, on disk: X.osw ----------------------------
+ * The reference's `-O preprocess` writes X.info / X.seq / X.desc (sequences.c:177-208) and every
+ * search re-lays X.seq out for the devices (assemble_db_chunks, sequences.c:828-1094).  Here the
+ * layout can be written once: osw_db_write_file builds the length-binned chunk streams of the whole
+ * canonical database (same arguments as osw_db_load; host only, needs no GPU) and stores them in a
+ * versioned little-endian file (oswald_b200/csrc/host/dbformat.h); osw_db_load_file maps it, copies
+ * the chunks of this context's shards (every n-th chunk) straight into pinned memory and uploads
+ * them - no per-residue work at search time.  One file serves any number of GPUs / ranks.
+ * OSW_E_IO: cannot open / write; OSW_E_FORMAT: not such a file, another version, or corrupt - the
+ * caller then falls back to osw_db_load from X.seq. */
+int osw_db_write_file(const char *path, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
+                      uint64_t max_chunk_residues);
+int osw_db_load_file(osw_ctx *ctx, const char *path, int shard_rank, int shard_count);
+/* Header of an X.osw file (every output pointer nullable). */
+int osw_db_file_info(const char *path, uint64_t *n_seqs, uint64_t *n_residues, uint64_t *n_chunks,
+                     uint32_t *max_len, uint32_t *version);
+
 /* Device window for the database, the GPU meaning of the reference's -k ("maximum chunk size in
  * FPGA (bytes)", arguments.c:113-117): when a GPU's share of the column stream is larger than
  * `bytes`, it is not kept resident; every search streams it from pinned host memory through two

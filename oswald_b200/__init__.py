@@ -5,4 +5,4 @@ Product code: the CUDA library (csrc/cuda, C ABI in include/oswald_cuda.h), the 
 and the bench.  Nothing here imports oracle/.
 """
 from .host import (ALPHABET, Database, Queries, Searcher, encode, load_query_sequences,  # noqa: F401
-                   matrix, matrix_names, preprocess_db, read_fasta)
+                   matrix, matrix_names, preprocess_db, read_fasta, write_db_file, db_file_info)

@@ -37,6 +37,10 @@ SYMBOLS = {
     "osw_init": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
     "osw_free": (None, [C.c_void_p]),
     "osw_db_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64]),
+    "osw_db_write_file": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "osw_db_load_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
+    "osw_db_file_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                   C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "osw_set_device_window": (C.c_int, [C.c_void_p, C.c_uint64]),
     "osw_db_upload": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "osw_db_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -171,6 +171,8 @@ extern "C" const char *osw_strerror(int code) {
         case OSW_E_NOMEM: return "out of memory";
         case OSW_E_STATE: return "call order error (database not loaded?)";
         case OSW_E_ARCH: return "device is not sm_100 (B200)";
+        case OSW_E_IO: return "file cannot be opened / written";
+        case OSW_E_FORMAT: return "not a database file of this format version";
     }
     return "unknown error";
 }
@@ -297,41 +299,32 @@ extern "C" int osw_set_device_window(osw_ctx *c, uint64_t bytes) {
     return OSW_OK;
 }
 
-extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
-                           int shard_rank, int shard_count, uint64_t max_chunk_residues) {
-    if (!c || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return OSW_E_ARG;
-    if (n_seqs && (!residues || !offsets)) return OSW_E_ARG;
-    if (n_seqs > 0xffffffffull) return OSW_E_ARG;
-    // The layout and the kernels rely on the canonical order (sequences.c:1130-1225): lengths
-    // ascending (a chunk's last sequence is its longest; empty sequences lead), offsets monotonic.
-    for (uint64_t i = 0, prev = 0; i < n_seqs; ++i) {
-        if (offsets[i + 1] < offsets[i]) { snprintf(g_err, sizeof g_err, "database offsets decrease at sequence %llu", (unsigned long long)i); return OSW_E_ARG; }
-        const uint64_t len = offsets[i + 1] - offsets[i];
-        if (len < prev || len > 0x7fffffffull) {
-            snprintf(g_err, sizeof g_err, "database sequence %llu (length %llu) breaks the ascending-length order",
-                     (unsigned long long)i, (unsigned long long)len);
-            return OSW_E_ARG;
-        }
-        prev = len;
-    }
-    // Work-unit size: 8192 residues for large databases (0.8 % pipeline fill per chunk; measured
-    // best together with the quarter-size chunks at the end of the queue); smaller for small
-    // databases so that every group of lanes on every SM gets several chunks.
+namespace {
+
+// Work-unit size: 8192 residues for large databases (0.8 % pipeline fill per chunk; measured best
+// together with the quarter-size chunks at the end of the queue); smaller for small databases so
+// that every group of lanes on every SM gets several chunks.
+uint32_t pick_chunk_cols(const Tunables &tune, uint64_t n_residues, uint64_t n_devices_total, uint64_t max_chunk_residues) {
     uint32_t chunk_cols = OSW_CHUNK_COLS_DEFAULT;
-    if (n_seqs) {
-        const uint64_t per_dev = offsets[n_seqs] / ((uint64_t)shard_count * (uint64_t)c->n_dev);
-        const uint64_t fit = per_dev / 25000;            // ~ 148 SMs x 12 warps x 8 groups x 2
-        if (fit < chunk_cols) chunk_cols = (uint32_t)(fit < 256 ? 256 : fit);
-    }
-    if (c->tune.chunk_cols) chunk_cols = c->tune.chunk_cols;             // experiments
+    const uint64_t per_dev = n_residues / (n_devices_total ? n_devices_total : 1);
+    const uint64_t fit = per_dev / 25000;            // ~ 148 SMs x 12 warps x 8 groups x 2
+    if (n_residues && fit < chunk_cols) chunk_cols = (uint32_t)(fit < 256 ? 256 : fit);
+    if (tune.chunk_cols) chunk_cols = tune.chunk_cols;             // experiments
     if (max_chunk_residues && max_chunk_residues < chunk_cols) chunk_cols = (uint32_t)max_chunk_residues;
+    return chunk_cols;
+}
+
+// Builds every GPU's shard with `build(device index, global shard, n_shards, allocator, user, out)`
+// - from the caller's canonical arrays or from a mapped X.osw file - straight into pinned host
+// memory (the source of every upload), allocates the device copies and uploads them.
+template <typename BuildShard>
+int load_shards(osw_ctx *c, uint64_t n_seqs_canon, int shard_rank, int shard_count, BuildShard build) {
     const uint32_t n_shards = (uint32_t)shard_count * (uint32_t)c->n_dev;
     c->db_loaded = false;
-    c->n_seqs_canon = n_seqs; c->n_seqs_local = 0; c->residues_local = 0; c->chunks_local = 0;
+    c->n_seqs_canon = n_seqs_canon; c->n_seqs_local = 0; c->residues_local = 0; c->chunks_local = 0;
     for (int i = 0; i < c->n_dev; ++i) {
         DevState &d = c->devs[i];
         free_db(d);
-        // the two streams are built straight into pinned host memory (the source of every upload)
         struct Pinned { uint8_t *ptr[2]; int n; } pinned = {{nullptr, nullptr}, 0};
         auto pinned_alloc = [](size_t bytes, void *user) -> void * {
             Pinned *pn = (Pinned *)user;
@@ -341,8 +334,7 @@ extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *
             return ptr;
         };
         CK(cudaSetDevice(d.dev));
-        const int brc = osw_shard_build_ex(residues, offsets, n_seqs, (uint32_t)shard_rank * c->n_dev + i, n_shards, chunk_cols,
-                                           0 /* the pair stream is made when a search first needs it */, pinned_alloc, &pinned, &d.shard);
+        const int brc = build((uint32_t)shard_rank * c->n_dev + i, n_shards, pinned_alloc, &pinned, &d.shard);
         if (brc != 0) {
             for (int k = 0; k < pinned.n; ++k) cudaFreeHost(pinned.ptr[k]);
             if (brc == -2) { snprintf(g_err, sizeof g_err, "the database holds a residue code outside 0..23"); return OSW_E_ARG; }
@@ -375,6 +367,84 @@ extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *
     }
     c->db_loaded = true;
     return OSW_OK;
+}
+
+}  // namespace
+
+extern "C" int osw_db_load(osw_ctx *c, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
+                           int shard_rank, int shard_count, uint64_t max_chunk_residues) {
+    if (!c || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return OSW_E_ARG;
+    if (n_seqs && (!residues || !offsets)) return OSW_E_ARG;
+    if (n_seqs > 0xffffffffull) return OSW_E_ARG;
+    // The layout and the kernels rely on the canonical order (sequences.c:1130-1225): lengths
+    // ascending (a chunk's last sequence is its longest; empty sequences lead), offsets monotonic.
+    for (uint64_t i = 0, prev = 0; i < n_seqs; ++i) {
+        if (offsets[i + 1] < offsets[i]) { snprintf(g_err, sizeof g_err, "database offsets decrease at sequence %llu", (unsigned long long)i); return OSW_E_ARG; }
+        const uint64_t len = offsets[i + 1] - offsets[i];
+        if (len < prev || len > 0x7fffffffull) {
+            snprintf(g_err, sizeof g_err, "database sequence %llu (length %llu) breaks the ascending-length order",
+                     (unsigned long long)i, (unsigned long long)len);
+            return OSW_E_ARG;
+        }
+        prev = len;
+    }
+    const uint32_t chunk_cols = pick_chunk_cols(c->tune, n_seqs ? offsets[n_seqs] : 0, (uint64_t)shard_count * c->n_dev, max_chunk_residues);
+    return load_shards(c, n_seqs, shard_rank, shard_count,
+                       [&](uint32_t shard, uint32_t n_shards, osw_alloc_fn alloc, void *user, osw_shard *out) {
+                           return osw_shard_build_ex(residues, offsets, n_seqs, shard, n_shards, chunk_cols,
+                                                     0 /* the pair stream is made when a search first needs it */, alloc, user, out);
+                       });
+}
+
+// ---- X.osw: the chunk streams on disk (dbformat.h) -------------------------------------------------
+extern "C" int osw_db_write_file(const char *path, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
+                                 uint64_t max_chunk_residues) {
+    if (!path || (n_seqs && (!residues || !offsets)) || n_seqs > 0xffffffffull) return OSW_E_ARG;
+    for (uint64_t i = 0, prev = 0; i < n_seqs; ++i) {
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] < prev) {
+            snprintf(g_err, sizeof g_err, "database sequence %llu breaks the ascending-length order", (unsigned long long)i);
+            return OSW_E_ARG;
+        }
+        prev = offsets[i + 1] - offsets[i];
+    }
+    Tunables tune;
+    tune.read();
+    const int rc = osw_dbfile_write(path, residues, offsets, n_seqs, pick_chunk_cols(tune, n_seqs ? offsets[n_seqs] : 0, 1, max_chunk_residues));
+    if (rc == -2) { snprintf(g_err, sizeof g_err, "the database holds a residue code outside 0..23"); return OSW_E_ARG; }
+    if (rc == -1) { snprintf(g_err, sizeof g_err, "cannot write %s", path); return OSW_E_IO; }
+    return rc ? OSW_E_NOMEM : OSW_OK;
+}
+
+static int dbfile_error(int rc, const char *path) {
+    snprintf(g_err, sizeof g_err, rc == -1 ? "cannot open %s" : rc == -2 ? "%s is not an X.osw file of format version 1" : "%s is truncated or corrupt", path);
+    return rc == -1 ? OSW_E_IO : OSW_E_FORMAT;
+}
+
+extern "C" int osw_db_file_info(const char *path, uint64_t *n_seqs, uint64_t *n_residues, uint64_t *n_chunks, uint32_t *max_len, uint32_t *version) {
+    if (!path) return OSW_E_ARG;
+    osw_dbfile f;
+    const int rc = osw_dbfile_open(path, &f);
+    if (rc) return dbfile_error(rc, path);
+    if (n_seqs) *n_seqs = f.h.n_seqs;
+    if (n_residues) *n_residues = f.h.n_residues;
+    if (n_chunks) *n_chunks = f.h.n_chunks;
+    if (max_len) *max_len = f.h.max_len;
+    if (version) *version = f.h.version;
+    osw_dbfile_close(&f);
+    return OSW_OK;
+}
+
+extern "C" int osw_db_load_file(osw_ctx *c, const char *path, int shard_rank, int shard_count) {
+    if (!c || !path || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return OSW_E_ARG;
+    osw_dbfile f;
+    int rc = osw_dbfile_open(path, &f);
+    if (rc) return dbfile_error(rc, path);
+    rc = load_shards(c, f.h.n_seqs, shard_rank, shard_count,
+                     [&](uint32_t shard, uint32_t n_shards, osw_alloc_fn alloc, void *user, osw_shard *out) {
+                         return osw_shard_from_file(&f, shard, n_shards, alloc, user, out);
+                     });
+    osw_dbfile_close(&f);
+    return rc;
 }
 
 extern "C" int osw_db_upload(osw_ctx *c, uint64_t *bytes) {

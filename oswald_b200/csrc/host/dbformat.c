@@ -5,8 +5,13 @@
  * other (OpenMP).  The two big buffers can come from a caller-supplied allocator (the CUDA
  * library passes pinned memory so that the streams are copied to the GPU straight from here). */
 #include "dbformat.h"
+#include <fcntl.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #define OSW_PAIR_ALIGN 64      /* columns */
 
@@ -215,6 +220,137 @@ void osw_shard_fill_pair(const osw_shard *s, const uint8_t *stream, uint8_t *pai
         const uint64_t pc_padded = ((uint64_t)ck->n_pair_cols + OSW_PAIR_ALIGN - 1) / OSW_PAIR_ALIGN * OSW_PAIR_ALIGN;
         memset(q, OSW_COL_PADBYTE, 2 * (pc_padded - ck->n_pair_cols));
     }
+}
+
+/* ---- X.osw ------------------------------------------------------------------------------------ */
+static uint64_t fnv1a(uint64_t h, const void *data, size_t n) {
+    const uint8_t *p = (const uint8_t *)data;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 0x100000001b3ull; }
+    return h;
+}
+
+int osw_dbfile_write(const char *path, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs, uint32_t chunk_cols) {
+    if (!chunk_cols) chunk_cols = OSW_CHUNK_COLS_DEFAULT;
+    osw_shard s;
+    const int rc = osw_shard_build_ex(residues, offsets, n_seqs, 0, 1, chunk_cols, 0, NULL, NULL, &s);      /* all chunks = shard 0 of 1 */
+    if (rc) return rc == -2 ? -2 : -3;
+    osw_dbfile_header h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, OSW_DBFILE_MAGIC, 8);
+    h.version = OSW_DBFILE_VERSION; h.chunk_cols = chunk_cols;
+    h.n_seqs = s.n_seqs; h.n_residues = s.n_residues; h.n_chunks = s.n_chunks; h.stream_bytes = s.stream_bytes;
+    h.max_len = s.max_len; h.chunk_align = OSW_CHUNK_ALIGN;
+    h.off_chunks = sizeof h;
+    h.off_lengths = h.off_chunks + h.n_chunks * sizeof(osw_chunk);
+    h.off_stream = (h.off_lengths + h.n_seqs * sizeof(uint32_t) + 4095) / 4096 * 4096;      /* page aligned: the stream is copied from the mapping */
+    h.file_bytes = h.off_stream + h.stream_bytes;
+    h.checksum = fnv1a(fnv1a(0xcbf29ce484222325ull, s.chunks, s.n_chunks * sizeof(osw_chunk)), s.seq_len, s.n_seqs * sizeof(uint32_t));
+    int ok = 0;
+    FILE *f = fopen(path, "wb");
+    if (f) {
+        static const uint8_t zeros[4096];
+        const size_t gap = (size_t)(h.off_stream - (h.off_lengths + h.n_seqs * sizeof(uint32_t)));
+        ok = fwrite(&h, sizeof h, 1, f) == 1 &&
+             (s.n_chunks == 0 || fwrite(s.chunks, sizeof(osw_chunk), s.n_chunks, f) == s.n_chunks) &&
+             (s.n_seqs == 0 || fwrite(s.seq_len, sizeof(uint32_t), s.n_seqs, f) == s.n_seqs) &&
+             (gap == 0 || fwrite(zeros, 1, gap, f) == gap) &&
+             (s.stream_bytes == 0 || fwrite(s.stream, 1, s.stream_bytes, f) == s.stream_bytes);
+        ok = (fclose(f) == 0) && ok;
+    }
+    osw_shard_free(&s);
+    return ok ? 0 : -1;
+}
+
+int osw_dbfile_open(const char *path, osw_dbfile *f) {
+    memset(f, 0, sizeof *f);
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return -1;
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return -1; }
+    if ((size_t)st.st_size < sizeof(osw_dbfile_header)) { close(fd); return -2; }
+    void *map = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) return -1;
+    memcpy(&f->h, map, sizeof f->h);
+    const osw_dbfile_header *h = &f->h;
+    int rc = 0;
+    if (memcmp(h->magic, OSW_DBFILE_MAGIC, 8) != 0 || h->version != OSW_DBFILE_VERSION || h->chunk_align != OSW_CHUNK_ALIGN) rc = -2;
+    else if (h->file_bytes > (uint64_t)st.st_size || h->off_chunks != sizeof *h ||
+             h->off_lengths != h->off_chunks + h->n_chunks * sizeof(osw_chunk) ||
+             h->off_stream < h->off_lengths + h->n_seqs * sizeof(uint32_t) || h->file_bytes != h->off_stream + h->stream_bytes ||
+             h->n_seqs > 0xffffffffull || h->n_chunks > 0xffffffffull || h->stream_bytes % OSW_CHUNK_ALIGN) rc = -3;
+    if (rc == 0) {
+        f->chunks = (const osw_chunk *)((const uint8_t *)map + h->off_chunks);
+        f->lengths = (const uint32_t *)((const uint8_t *)map + h->off_lengths);
+        f->stream = (const uint8_t *)map + h->off_stream;
+        if (fnv1a(fnv1a(0xcbf29ce484222325ull, f->chunks, h->n_chunks * sizeof(osw_chunk)), f->lengths, h->n_seqs * sizeof(uint32_t)) != h->checksum) rc = -3;
+        /* every chunk lies inside the stream and inside the sequence list */
+        for (uint64_t k = 0; rc == 0 && k < h->n_chunks; ++k) {
+            const osw_chunk *ck = &f->chunks[k];
+            const uint64_t padded = ((uint64_t)ck->n_cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
+            if (ck->stream_off % OSW_CHUNK_ALIGN || ck->stream_off + padded > h->stream_bytes || (uint64_t)ck->canon0 + ck->n_seqs > h->n_seqs || ck->seq0 != ck->canon0) rc = -3;
+        }
+    }
+    if (rc) { munmap(map, (size_t)st.st_size); memset(f, 0, sizeof *f); return rc; }
+    f->map = map; f->map_size = (size_t)st.st_size;
+    return 0;
+}
+
+void osw_dbfile_close(osw_dbfile *f) {
+    if (f && f->map) munmap(f->map, f->map_size);
+    if (f) memset(f, 0, sizeof *f);
+}
+
+int osw_shard_from_file(const osw_dbfile *f, uint32_t shard, uint32_t n_shards, osw_alloc_fn alloc, void *alloc_user, osw_shard *out) {
+    if (!f || !f->map || !out || !n_shards || shard >= n_shards) return -1;
+    memset(out, 0, sizeof *out);
+    const uint64_t nc = f->h.n_chunks;
+    /* the file's directory is in descending order; the walk (= dealing) order is ascending: walk index c = nc-1-k */
+    uint64_t mine = 0, seqs = 0, bytes = 0, cols = 0;
+    for (uint64_t c = shard; c < nc; c += n_shards) {
+        const osw_chunk *ck = &f->chunks[nc - 1 - c];
+        ++mine; seqs += ck->n_seqs; cols += ck->n_cols;
+        bytes += ((uint64_t)ck->n_cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
+    }
+    out->n_seqs = seqs; out->n_residues = cols; out->stream_bytes = bytes; out->n_chunks = (uint32_t)mine;
+    out->external_streams = alloc != NULL;
+    out->stream = (uint8_t *)(alloc ? alloc(bytes ? bytes : 1, alloc_user) : malloc(bytes ? bytes : 1));
+    out->chunks  = (osw_chunk *)malloc((mine ? mine : 1) * sizeof(osw_chunk));
+    out->canon   = (uint32_t *)malloc((seqs ? seqs : 1) * sizeof(uint32_t));
+    out->seq_off = (uint64_t *)malloc((seqs ? seqs : 1) * sizeof(uint64_t));
+    out->seq_len = (uint32_t *)malloc((seqs ? seqs : 1) * sizeof(uint32_t));
+    if (!out->stream || !out->chunks || !out->canon || !out->seq_off || !out->seq_len) { osw_shard_free(out); return -1; }
+    /* layout (serial, cheap), then the copies (parallel) */
+    uint64_t byte_cursor = 0, seq_cursor = 0, n = 0;
+    for (uint64_t c = shard; c < nc; c += n_shards, ++n) {
+        const osw_chunk *src = &f->chunks[nc - 1 - c];
+        osw_chunk *ck = &out->chunks[mine - 1 - n];                 /* stored descending */
+        *ck = *src;
+        ck->stream_off = byte_cursor; ck->seq0 = (uint32_t)seq_cursor; ck->pair_off = 0; ck->n_pair_cols = 0; ck->reserved = 0;
+        byte_cursor += ((uint64_t)src->n_cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
+        seq_cursor += src->n_seqs;
+        if (src->n_seqs) {
+            const uint32_t last = f->lengths[(uint64_t)src->canon0 + src->n_seqs - 1];      /* longest: order is ascending */
+            if (last > out->max_len) out->max_len = last;
+        }
+    }
+    const long long n_mine = (long long)mine;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long k = 0; k < n_mine; ++k) {
+        const osw_chunk *ck = &out->chunks[k];
+        const uint64_t c = (uint64_t)shard + (uint64_t)(n_mine - 1 - k) * n_shards;
+        const osw_chunk *src = &f->chunks[nc - 1 - c];
+        const uint64_t padded = ((uint64_t)ck->n_cols + OSW_CHUNK_ALIGN - 1) / OSW_CHUNK_ALIGN * OSW_CHUNK_ALIGN;
+        memcpy(out->stream + ck->stream_off, f->stream + src->stream_off, padded);
+        uint64_t off = ck->stream_off;
+        for (uint32_t i = 0; i < ck->n_seqs; ++i) {
+            const uint32_t canon = ck->canon0 + i, len = f->lengths[canon];
+            out->canon[ck->seq0 + i] = canon; out->seq_len[ck->seq0 + i] = len; out->seq_off[ck->seq0 + i] = off;
+            off += len;
+        }
+    }
+    if (build_pair_directory(out, f->h.chunk_cols) != 0) { osw_shard_free(out); return -1; }
+    return 0;
 }
 
 void osw_shard_free(osw_shard *s) {

@@ -86,6 +86,44 @@ typedef void *(*osw_alloc_fn)(size_t bytes, void *user);
 int osw_shard_build_ex(const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs,
                        uint32_t shard, uint32_t n_shards, uint32_t chunk_cols, int with_pair,
                        osw_alloc_fn alloc, void *alloc_user, osw_shard *out);
+/* ---- the same layout on disk: X.osw ----------------------------------------------------------
+ * `-O preprocess` writes it next to the reference's triple (X.info / X.seq / X.desc, sequences.c:177-208);
+ * a search then maps it and copies chunk streams straight into pinned memory instead of re-laying
+ * the database out (flags, padding, directories) at every start.  One file serves any number of
+ * GPUs: it holds ALL chunks of the canonical database in order, and shard s of n takes every n-th.
+ * Little-endian, versioned; a reader rejects other versions, and the caller falls back to X.seq.
+ *   header   128 bytes (osw_dbfile_header)
+ *   chunks   n_chunks x osw_chunk, DESCENDING length order, offsets relative to the stream section
+ *   lengths  n_seqs x uint32, canonical order
+ *   stream   stream_bytes: chunk column streams back to back, each padded to OSW_CHUNK_ALIGN  */
+#define OSW_DBFILE_MAGIC "OSWB200"         /* 7 characters + NUL */
+#define OSW_DBFILE_VERSION 1u
+typedef struct osw_dbfile_header {
+    char     magic[8];
+    uint32_t version;
+    uint32_t chunk_cols;       /* the work-unit size the chunks were cut with */
+    uint64_t n_seqs, n_residues, n_chunks, stream_bytes;
+    uint32_t max_len, chunk_align;
+    uint64_t off_chunks, off_lengths, off_stream, file_bytes;
+    uint64_t checksum;         /* FNV-1a of the chunk directory and the lengths */
+    uint8_t  reserved[32];
+} osw_dbfile_header;
+typedef struct osw_dbfile {
+    osw_dbfile_header h;
+    const osw_chunk *chunks;
+    const uint32_t  *lengths;
+    const uint8_t   *stream;
+    void *map; size_t map_size;
+} osw_dbfile;
+/* 0, -1 cannot create / write, -2 bad residue code, -3 allocation failure */
+int  osw_dbfile_write(const char *path, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seqs, uint32_t chunk_cols);
+/* 0, -1 cannot open, -2 not an X.osw file of this version, -3 truncated or corrupt */
+int  osw_dbfile_open(const char *path, osw_dbfile *f);
+void osw_dbfile_close(osw_dbfile *f);
+/* Shard `shard` of `n_shards` from a mapped file: the same osw_shard osw_shard_build_ex makes from the
+ * canonical arrays with the file's chunk_cols (tested).  0 or -1. */
+int  osw_shard_from_file(const osw_dbfile *f, uint32_t shard, uint32_t n_shards, osw_alloc_fn alloc, void *alloc_user, osw_shard *out);
+
 /* Fills pair[2 * s->pair_cols] from the shard's plain stream (for a deferred pair stream). */
 void osw_shard_fill_pair(const osw_shard *s, const uint8_t *stream, uint8_t *pair);
 void osw_shard_free(osw_shard *s);

@@ -64,6 +64,7 @@ typedef struct osw_fasta {
     char     *title_pool;
 } osw_fasta;
 int  osw_fasta_read(const char *path, osw_fasta *out);      /* 0, or -1 (cannot open) / -2 (memory) */
+int  osw_fasta_read_mt(const char *path, osw_fasta *out, int n_threads);
 void osw_fasta_free(osw_fasta *f);
 /* perm[k] = record at canonical position k: stable ascending length (sequences.c:1130-1225) */
 uint64_t *osw_length_order(const osw_fasta *f);

@@ -6,6 +6,7 @@
  *   X.desc  N lines ">title", in that order          (:137-138)
  * and the loader of that triple for `-O search`. */
 #include "oswald_host.h"
+#include "oswald_cuda.h"
 #include <fcntl.h>
 #include <stdlib.h>
 #include <string.h>
@@ -14,9 +15,8 @@
 #include <unistd.h>
 
 int preprocess_db(const char *input_filename, const char *out_filename, int n_procs) {
-    (void)n_procs;
     osw_fasta fa;
-    int rc = osw_fasta_read(input_filename, &fa);
+    int rc = osw_fasta_read_mt(input_filename, &fa, n_procs);
     if (rc == -1) { printf("OSWALD: An error occurred while opening input sequence file.\n"); return 2; }
     if (rc) { printf("OSWALD: An error occurred while allocating memory for sequences.\n"); return 1; }
     for (uint64_t i = 0; i < fa.n; ++i)
@@ -26,11 +26,27 @@ int preprocess_db(const char *input_filename, const char *out_filename, int n_pr
             return 1;
         }
     uint64_t *perm = osw_length_order(&fa);
-    if (!perm) { printf("OSWALD: An error occurred while allocating memory.\n"); osw_fasta_free(&fa); return 1; }
+    /* the canonical database in memory: lengths, offsets, residues in sorted order */
+    uint16_t *lens = (uint16_t *)malloc((fa.n ? fa.n : 1) * sizeof(uint16_t));
+    uint64_t *coff = (uint64_t *)malloc((fa.n + 1) * sizeof(uint64_t));
+    uint8_t *cres = (uint8_t *)malloc(fa.n_residues ? fa.n_residues : 1);
+    if (!perm || !lens || !coff || !cres) {
+        printf("OSWALD: An error occurred while allocating memory.\n");
+        free(perm); free(lens); free(coff); free(cres); osw_fasta_free(&fa);
+        return 1;
+    }
+    coff[0] = 0;
+    for (uint64_t k = 0; k < fa.n; ++k) {
+        lens[k] = (uint16_t)(fa.offsets[perm[k] + 1] - fa.offsets[perm[k]]);
+        coff[k + 1] = coff[k] + lens[k];
+    }
+#pragma omp parallel for schedule(static) num_threads(n_procs > 0 ? n_procs : 1)
+    for (long long k = 0; k < (long long)fa.n; ++k) memcpy(cres + coff[k], fa.residues + fa.offsets[perm[k]], lens[k]);
+    int ret = 0;
     char filename[4096];
     snprintf(filename, sizeof filename, "%s.desc", out_filename);
     FILE *titles_file = fopen(filename, "w");
-    if (!titles_file) { printf("OSWALD: An error occurred while opening sequence header file.\n"); return 2; }
+    if (!titles_file) { printf("OSWALD: An error occurred while opening sequence header file.\n"); ret = 2; goto done; }
     int max_title_length = 0;
     for (uint64_t k = 0; k < fa.n; ++k) {
         const char *t = fa.titles[perm[k]];
@@ -41,20 +57,26 @@ int preprocess_db(const char *input_filename, const char *out_filename, int n_pr
     fclose(titles_file);
     snprintf(filename, sizeof filename, "%s.info", out_filename);
     FILE *info_file = fopen(filename, "w");
-    if (!info_file) { printf("OSWALD: An error occurred while opening info file.\n"); return 2; }
+    if (!info_file) { printf("OSWALD: An error occurred while opening info file.\n"); ret = 2; goto done; }
     fprintf(info_file, "%ld %ld %d", (long)fa.n, (long)fa.n_residues, max_title_length);
     fclose(info_file);
     snprintf(filename, sizeof filename, "%s.seq", out_filename);
     FILE *bin_file = fopen(filename, "wb");
-    if (!bin_file) { printf("OSWALD: An error occurred while opening sequence file.\n"); return 2; }
-    uint16_t *lens = (uint16_t *)malloc((fa.n ? fa.n : 1) * sizeof(uint16_t));
-    for (uint64_t k = 0; k < fa.n; ++k) lens[k] = (uint16_t)(fa.offsets[perm[k] + 1] - fa.offsets[perm[k]]);
+    if (!bin_file) { printf("OSWALD: An error occurred while opening sequence file.\n"); ret = 2; goto done; }
     fwrite(lens, sizeof(uint16_t), fa.n, bin_file);
-    for (uint64_t k = 0; k < fa.n; ++k) fwrite(fa.residues + fa.offsets[perm[k]], 1, lens[k], bin_file);
+    fwrite(cres, 1, fa.n_residues, bin_file);
     fclose(bin_file);
-    free(lens); free(perm);
+    /* the same database in its device layout (chunk column streams, directories): X.osw.  A search
+     * uses it when it is there and falls back to X.seq otherwise. */
+    snprintf(filename, sizeof filename, "%s.osw", out_filename);
+    if ((rc = osw_db_write_file(filename, cres, coff, fa.n, 0)) != OSW_OK) {
+        printf("OSWALD: cannot write %s: %s (%s).\n", filename, osw_strerror(rc), osw_last_error());
+        ret = 2;
+    }
+done:
+    free(lens); free(coff); free(cres); free(perm);
     osw_fasta_free(&fa);
-    return 0;
+    return ret;
 }
 
 int load_database(const char *prefix, osw_database *db) {

@@ -183,6 +183,11 @@ class Searcher:
                                        shard_rank, shard_count, max_chunk_residues), "osw_db_load")
         self.n_seqs = db.n_seqs
 
+    def load_db_file(self, path, shard_rank=0, shard_count=1):
+        """Load a database from its X.osw file (written by write_db_file / `-O preprocess`)."""
+        capi.check(self._L.osw_db_load_file(self._ctx, str(path).encode(), shard_rank, shard_count), "osw_db_load_file")
+        self.n_seqs = db_file_info(path)["n_seqs"]
+
     def upload_db(self):
         """Host -> device copy of the resident chunk streams again; returns bytes copied."""
         n = C.c_uint64()
@@ -209,6 +214,18 @@ class Searcher:
         if all_scores:
             return out, tm.as_dict(), scores
         return out, tm.as_dict()
+
+
+def write_db_file(path, db, max_chunk_residues=0):
+    """The canonical database in its device layout, on disk (X.osw).  Host only: needs no GPU."""
+    capi.check(capi.lib().osw_db_write_file(str(path).encode(), _vp(db.residues), _vp(db.offsets), db.n_seqs, max_chunk_residues),
+               "osw_db_write_file")
+
+
+def db_file_info(path):
+    a, b, c, m, v = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint32(), C.c_uint32()
+    capi.check(capi.lib().osw_db_file_info(str(path).encode(), C.byref(a), C.byref(b), C.byref(c), C.byref(m), C.byref(v)), "osw_db_file_info")
+    return {"n_seqs": a.value, "n_residues": b.value, "n_chunks": c.value, "max_len": m.value, "version": v.value}
 
 
 def merge_hits(lists, top):

@@ -282,6 +282,54 @@ def test_cli_report_matches_the_reference(built, tmp_path):
                 assert [[int(l.split("\t")[0]), l.split("\t")[1]] for l in lines] == h["top"]
             dump = np.fromfile(tmp_path / "dump.bin", dtype=np.int32).reshape(-1, meta["n_seqs"])
             assert np.array_equal(dump, run["score_matrix"])
+            assert "X.osw" in out                      # the search used the device layout -O preprocess wrote
+        # without X.osw (a database preprocessed by the reference itself): laid out from X.seq, same report
+        run = meta["runs"][0]
+        legacy = subprocess.run([cli, "-O", "search", "-q", "q.fasta", "-d", "db", "-s", run["matrix"], "-g", str(run["gap_open"]),
+                                 "-e", str(run["gap_extend"]), "-r", str(meta["top"])], cwd=tmp_path, check=True, capture_output=True,
+                                text=True, env=dict(os.environ, OSW_NO_DBFILE="1")).stdout
+        first = subprocess.run([cli, "-O", "search", "-q", "q.fasta", "-d", "db", "-s", run["matrix"], "-g", str(run["gap_open"]),
+                                "-e", str(run["gap_extend"]), "-r", str(meta["top"])], cwd=tmp_path, check=True, capture_output=True, text=True).stdout
+        assert "X.seq" in legacy and legacy.split("\nSearch date:")[0] == first.split("\nSearch date:")[0]
+
+
+def test_database_from_its_file(built, tmp_path):
+    """osw_db_load_file (X.osw: the chunk streams from disk) gives the same scores and hits as
+    osw_db_load from the canonical arrays, unsharded and as two ranks' shards."""
+    from oswald_b200.host import merge_hits
+    rng = np.random.default_rng(515)
+    seqs = rand_seqs(rng, 2500, 0, 400) + [AA[rng.integers(0, 20, size=n)] for n in (3000, 20000)]
+    q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (64, 300, 1400)])
+    seqs[11] = q.query(1).copy()
+    db = make_db(seqs)
+    want = oracle_scores(q, db, "blosum62", 10, 2)
+    path = tmp_path / "db.osw"
+    ob.write_db_file(path, db, max_chunk_residues=2048)
+    with ob.Searcher(1) as s:
+        s.load_db_file(path)
+        assert s.stats()["n_seqs"] == db.n_seqs and s.stats()["residues"] == db.n_residues
+        for mode in MODES.values():
+            check(s, db, q, "blosum62", 10, 2, 10, mask=mode, want=want)
+        s.set_kernels(capi.OSW_K_DEFAULT)
+        s.upload_db()
+        check(s, db, q, "blosum62", 10, 2, 10, want=want)
+    parts, total = [], np.zeros_like(want)
+    for rank in range(2):
+        with ob.Searcher(1) as s:
+            s.load_db_file(path, shard_rank=rank, shard_count=2)
+            hits, tm, sc = s.search(q, ob.matrix("blosum62"), 10, 2, top=10, all_scores=True)
+            parts.append(hits)
+            total += sc
+    assert np.array_equal(total, want)
+    for qi in range(q.n):
+        idx, sc = O.top_r(want[qi], 10)
+        assert merge_hits([parts[0][qi], parts[1][qi]], 10) == [(int(a), int(b)) for a, b in zip(sc, idx)]
+    with ob.Searcher(1) as s:
+        (tmp_path / "bad.osw").write_bytes(path.read_bytes()[:5000])
+        with pytest.raises(capi.OswError):
+            s.load_db_file(tmp_path / "bad.osw")
+        s.load_db(db)                              # the context stays usable
+        check(s, db, q, "blosum62", 10, 2, 10, want=want)
 
 
 def test_two_gpus_in_one_context(built):
@@ -377,17 +425,23 @@ def test_cli_two_gpus_same_report(built, tmp_path):
 
 def test_segmented_bottom_rows(built, monkeypatch):
     """Several passes with a bottom-row buffer that holds only a few chunks at a time."""
-    monkeypatch.setenv("OSW_BOUND_BUDGET_COLS", "2048")
     rng = np.random.default_rng(88)
     seqs = rand_seqs(rng, 1500, 1, 400) + [AA[rng.integers(0, 20, size=n)] for n in (3000, 70000)]
     q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (1500, 2900, 1400)])
     seqs[7] = q.query(2).copy()
     db = make_db(seqs)
+    want = oracle_scores(q, db, "blosum62", 10, 2)
+    unsegmented = {}
+    with ob.Searcher(1) as s:                                   # (the switch is read when a context is made)
+        s.load_db(db, max_chunk_residues=512)
+        for name, mode in MODES.items():
+            unsegmented[name] = check(s, db, q, "blosum62", 10, 2, 10, mask=mode, want=want)["score_launches"]
+    monkeypatch.setenv("OSW_BOUND_BUDGET_COLS", "2048")
     with ob.Searcher(1) as s:
         s.load_db(db, max_chunk_residues=512)
-        for mode in MODES.values():
-            tm = check(s, db, q, "blosum62", 10, 2, 10, mask=mode)
-            assert tm["score_launches"] >= 12    # several segments x passes (unsegmented: 5 or fewer)
+        for name, mode in MODES.items():
+            tm = check(s, db, q, "blosum62", 10, 2, 10, mask=mode, want=want)
+            assert tm["score_launches"] >= 2 * unsegmented[name]          # at least two segments x passes
 
 
 def test_query_batches(built, monkeypatch):

@@ -387,3 +387,117 @@ def test_scoring_kernel_schedule_is_the_measured_one(built):
         assert got[name]["local_memory_ops"] == 0, name
         assert got[name]["viaddmnmx_u16x2"] == fp["viaddmnmx_u16x2"] and got[name]["vimnmx3_u16x2"] == fp["vimnmx3_u16x2"], name
         assert got[name] == fp, "%s: inner loop changed (%s -> %s)" % (name, fp, got[name])
+
+
+# ---- X.osw: the device layout on disk ---------------------------------------------------------
+class DbFileHeader(C.Structure):
+    _fields_ = [("magic", C.c_char * 8), ("version", C.c_uint32), ("chunk_cols", C.c_uint32),
+                ("n_seqs", C.c_uint64), ("n_residues", C.c_uint64), ("n_chunks", C.c_uint64), ("stream_bytes", C.c_uint64),
+                ("max_len", C.c_uint32), ("chunk_align", C.c_uint32),
+                ("off_chunks", C.c_uint64), ("off_lengths", C.c_uint64), ("off_stream", C.c_uint64), ("file_bytes", C.c_uint64),
+                ("checksum", C.c_uint64), ("reserved", C.c_uint8 * 32)]
+
+
+class DbFile(C.Structure):
+    _fields_ = [("h", DbFileHeader), ("chunks", C.POINTER(Chunk)), ("lengths", C.POINTER(C.c_uint32)),
+                ("stream", C.POINTER(C.c_uint8)), ("map", C.c_void_p), ("map_size", C.c_size_t)]
+
+
+def shard_fields(s):
+    """Everything a shard holds, as comparable Python values."""
+    arr = lambda p, n, t: np.ctypeslib.as_array(p, shape=(max(n, 1),))[:n].astype(t).tolist() if n else []
+    chunk = lambda ck: (ck.stream_off, ck.n_cols, ck.n_seqs, ck.seq0, ck.canon0, ck.pair_off, ck.n_pair_cols)
+    return {"n_seqs": s.n_seqs, "n_residues": s.n_residues, "stream_bytes": s.stream_bytes, "n_chunks": s.n_chunks, "max_len": s.max_len,
+            "stream": bytes(np.ctypeslib.as_array(s.stream, shape=(max(s.stream_bytes, 1),))[:s.stream_bytes]),
+            "chunks": [chunk(s.chunks[k]) for k in range(s.n_chunks)], "pair_cols": s.pair_cols,
+            "pair_chunks": [chunk(s.pair_chunks[k]) for k in range(s.n_pair_chunks)],
+            "canon": arr(s.canon, s.n_seqs, np.int64), "seq_off": arr(s.seq_off, s.n_seqs, np.int64), "seq_len": arr(s.seq_len, s.n_seqs, np.int64)}
+
+
+@pytest.mark.parametrize("n_seqs,lo,hi", [(0, 1, 2), (1, 5, 6), (40, 0, 3), (3000, 0, 300), (500, 200, 5000)])
+def test_db_file_round_trip(built, tmp_path, n_seqs, lo, hi):
+    """osw_db_write_file -> osw_dbfile_open -> osw_shard_from_file gives, for every shard of 1, 2 and 8,
+    exactly the shard osw_shard_build_ex lays out from the canonical arrays (streams, directories, tables)."""
+    rng = np.random.default_rng(n_seqs + hi)
+    db = random_db(rng, n_seqs, lo, hi) if n_seqs else ob.Database(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    path = tmp_path / "db.osw"
+    ob.write_db_file(path, db, max_chunk_residues=1024)
+    info = ob.db_file_info(path)
+    assert (info["n_seqs"], info["n_residues"], info["version"]) == (db.n_seqs, db.n_residues, 1)
+    assert info["max_len"] == (int(np.diff(db.offsets.astype(np.int64)).max()) if db.n_seqs else 0)
+    L = built
+    L.osw_dbfile_open.argtypes = [C.c_char_p, C.POINTER(DbFile)]
+    L.osw_dbfile_close.argtypes = [C.POINTER(DbFile)]
+    L.osw_shard_from_file.argtypes = [C.POINTER(DbFile), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(Shard)]
+    L.osw_shard_free.argtypes = [C.POINTER(Shard)]
+    f = DbFile()
+    assert L.osw_dbfile_open(str(path).encode(), C.byref(f)) == 0
+    assert f.h.off_stream % 4096 == 0 and f.h.file_bytes == os.path.getsize(path)
+    for n_shards in (1, 2, 8):
+        for sh in range(n_shards):
+            a = build_shard(L, db, sh, n_shards, f.h.chunk_cols)
+            b = Shard()
+            assert L.osw_shard_from_file(C.byref(f), sh, n_shards, None, None, C.byref(b)) == 0
+            fa, fb = shard_fields(a), shard_fields(b)
+            for key in fa:
+                assert fa[key] == fb[key], (n_shards, sh, key)
+            L.osw_shard_free(C.byref(a)); L.osw_shard_free(C.byref(b))
+    L.osw_dbfile_close(C.byref(f))
+
+
+def test_db_file_rejects_damage(built, tmp_path):
+    """Another version, a truncated file, a flipped directory byte, a file that is something else:
+    OSW_E_FORMAT / OSW_E_IO with a message, never a crash (the caller then falls back to X.seq)."""
+    rng = np.random.default_rng(3)
+    db = random_db(rng, 400, 1, 200)
+    path = tmp_path / "db.osw"
+    ob.write_db_file(path, db)
+    good = path.read_bytes()
+    cases = {"version": good[:8] + (2).to_bytes(4, "little") + good[12:], "truncated": good[:len(good) // 2],
+             "directory": good[:200] + bytes([good[200] ^ 1]) + good[201:], "not_osw": b"hello world" * 50, "tiny": b"OSW"}
+    for name, blob in cases.items():
+        bad = tmp_path / (name + ".osw")
+        bad.write_bytes(blob)
+        with pytest.raises(capi.OswError) as e:
+            ob.db_file_info(bad)
+        assert "format" in str(e.value) or "corrupt" in str(e.value), name
+    with pytest.raises(capi.OswError):
+        ob.db_file_info(tmp_path / "missing.osw")
+    unsorted = ob.Database(AA[rng.integers(0, 20, size=60)], np.array([0, 40, 60], dtype=np.uint64))
+    with pytest.raises(capi.OswError):
+        ob.write_db_file(tmp_path / "u.osw", unsorted)
+
+
+def test_cli_preprocess_threads_and_db_file(built, tmp_path):
+    """`-O preprocess -c N`: the parallel FASTA scan writes the same files for every thread count
+    (blocks cut mid-record, CRLF, junk before the first record), and X.osw holds the same database."""
+    import subprocess
+    rng = np.random.default_rng(12)
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYBXZJ", dtype=np.uint8)
+    recs = []
+    for i in range(3000):
+        n = int(rng.integers(0, 900)) if i % 50 else 5000
+        seq = letters[rng.integers(0, 24, size=n)].tobytes().decode()
+        width = int(rng.choice([60, 70, 1000]))
+        eol = "\r\n" if i % 7 == 0 else "\n"
+        recs.append(">rec%d some title %s%s" % (i, "x" * int(rng.integers(0, 40)), eol) +
+                    "".join(seq[k:k + width] + eol for k in range(0, n, width)))
+    text = "junk line before the first record\n\n" + "".join(recs)
+    (tmp_path / "in.fasta").write_bytes(text.encode()[:-1])              # (no newline at the end)
+    assert len(text) > 3 * (1 << 20) / 2                                 # several 1 MiB blocks
+    outs = {}
+    for c in ("1", "3", "8"):
+        subprocess.run([_cli(), "-O", "preprocess", "-i", "in.fasta", "-o", "db" + c, "-c", c], cwd=tmp_path, check=True)
+        outs[c] = {ext: (tmp_path / ("db%s.%s" % (c, ext))).read_bytes() for ext in ("info", "seq", "desc", "osw")}
+    assert outs["1"] == outs["3"] == outs["8"]
+    titles, seqs = ob.read_fasta(tmp_path / "in.fasta")
+    assert len(titles) == 3000
+    db = ob.Database.from_lengths(np.array([len(s) for s in seqs], dtype=np.uint64), ob.encode("".join(seqs)), titles)
+    raw = outs["1"]["seq"]
+    assert np.array_equal(np.frombuffer(raw[:2 * db.n_seqs], dtype="<u2"), np.diff(db.offsets.astype(np.int64)))
+    assert np.array_equal(np.frombuffer(raw[2 * db.n_seqs:], dtype=np.uint8), db.residues)
+    assert [l.rstrip("\r\n")[1:] for l in outs["1"]["desc"].decode().splitlines()] == [t.rstrip("\r") for t in db.titles]
+    info = ob.db_file_info(tmp_path / "db1.osw")
+    assert (info["n_seqs"], info["n_residues"]) == (db.n_seqs, db.n_residues)
+    ob.write_db_file(tmp_path / "again.osw", db)
+    assert (tmp_path / "again.osw").read_bytes() == outs["1"]["osw"]
