@@ -27,7 +27,7 @@ namespace {
 constexpr uint32_t MAX_LAUNCH_SLOTS = 4096;
 constexpr uint32_t FLAG_CAPACITY_MIN = 1u << 16;
 
-struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; uint32_t express; uint32_t slot; };
+struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; uint32_t express; uint32_t slot; uint32_t x_chunks, x_ctas; int x_R; };
 
 struct DevState {
     int dev = -1, n_sms = 0;
@@ -57,6 +57,8 @@ struct DevState {
     int2 *d_scratch = nullptr; size_t scratch_cap = 0;
     uint2 *d_bound = nullptr; size_t bound_cap = 0;   // bottom rows handed from pass to pass (in place), one segment of chunks at a time
     unsigned char *d_profile = nullptr;        // the current pass's profile table image
+    unsigned char *d_profile_x = nullptr;      // ... of a long-chunk launch beside it
+    uint32_t *d_first_table_x = nullptr;
     uint32_t *d_first_table = nullptr;         // the current pass's first-chunk deal (CTAs x warps)
     uint2 *d_pairs = nullptr; uint32_t pairs_cap = 0;
     uint32_t *d_counters = nullptr;            // [0] flagged count, [1..] chunk counters per launch
@@ -137,6 +139,7 @@ struct Tunables {
     double   express_ratio = 1.5;       // OSW_EXPRESS_RATIO
     int      force_g = 0;               // OSW_MIN_G: force a group width for single-pass plans
     int      rmax = 0;                  // OSW_RMAX: rows per lane of the full-height passes (0 = default)
+    int      long_chunks = -1;          // OSW_LONG_CHUNKS: force the number of chunks of the long-chunk launch (0 = never)
     bool     trace = false;             // OSW_TRACE: per-launch report on stderr
     void read() {
         if (const char *e = getenv("OSW_CHUNK_COLS")) { const int v = atoi(e); if (v >= 64) chunk_cols = (uint32_t)v; }
@@ -147,6 +150,7 @@ struct Tunables {
         if (const char *e = getenv("OSW_EXPRESS_RATIO")) express_ratio = atof(e);
         if (const char *e = getenv("OSW_MIN_G")) force_g = atoi(e);
         if (const char *e = getenv("OSW_RMAX")) rmax = atoi(e);
+        if (const char *e = getenv("OSW_LONG_CHUNKS")) long_chunks = atoi(e);
         trace = getenv("OSW_TRACE") != nullptr;
     }
 };
@@ -244,6 +248,8 @@ extern "C" int osw_init(int n_devices, const int *devices, osw_ctx **out) {
         if ((e = cudaMalloc(&d.d_matrix, 24 * 32)) != cudaSuccess ||
             (e = cudaMalloc(&d.d_profile, OSW_PROFILE_BYTES)) != cudaSuccess ||
             (e = cudaMalloc(&d.d_first_table, 1024 * 16 * sizeof(uint32_t))) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_profile_x, OSW_PROFILE_BYTES)) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_first_table_x, 1024 * 16 * sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_counters, (1 + MAX_LAUNCH_SLOTS) * sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_task_counter, 2 * sizeof(unsigned long long))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_cycles, MAX_LAUNCH_SLOTS * sizeof(unsigned long long))) != cudaSuccess ||
@@ -265,7 +271,7 @@ extern "C" void osw_free(osw_ctx *c) {
         if (d.st) cudaStreamSynchronize(d.st);
         free_db(d);
         cudaFree(d.d_scores); cudaFree(d.d_queries); cudaFree(d.d_qoff); cudaFree(d.d_matrix); cudaFree(d.d_scratch);
-        cudaFree(d.d_profile); cudaFree(d.d_first_table);
+        cudaFree(d.d_profile); cudaFree(d.d_first_table); cudaFree(d.d_profile_x); cudaFree(d.d_first_table_x);
         cudaFree(d.d_pairs); cudaFree(d.d_counters); cudaFree(d.d_task_counter); cudaFree(d.d_cycles);
         cudaFree(d.topr.hist); cudaFree(d.topr.prefix); cudaFree(d.topr.remaining); cudaFree(d.topr.out_count); cudaFree(d.topr.out_keys);
         if (d.h_keys) cudaFreeHost(d.h_keys);
@@ -506,19 +512,23 @@ constexpr int MAX_PASSES = 2048;
 struct LaunchModel {
     double issue, alone, contended, t_pipe;
     int groups, warps_per_scheduler;
-    LaunchModel(int G, int R, bool pd, double cols, int n_sms) {
+    // n_chunks: chunks of the launch (0 = plenty).  On a database of few chunks not every warp of a
+    // scheduler has work, and a chunk is walked faster than among three busy neighbours.
+    LaunchModel(int G, int R, bool pd, double cols, int n_sms, double n_chunks = 0.0) {
         groups = 32 / G;
         warps_per_scheduler = R > 32 ? 3 : 4;                       // 384- / 512-thread CTAs
         issue = (pd ? 11.7 : 9.0) * R + 45.0;
         alone = 140.0 + 7.0 * R;
-        contended = std::max(alone, warps_per_scheduler * issue);
+        double busy = warps_per_scheduler;
+        if (n_chunks > 0.0) busy = std::min(busy, std::max(1.0, n_chunks / ((double)groups * std::max(n_sms, 1) * 4.0)));
+        contended = std::max(alone, busy * issue);
         t_pipe = cols / ((double)groups * std::max(n_sms, 1) * 4.0) * issue;
     }
 };
 
 int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32_t *q_off, int nq,
                    const int8_t *matrix, int go, int ge, uint32_t top_r, bool want_all,
-                   const std::vector<OswPass> &passes,
+                   const std::vector<OswPass> &passes, const OswPass *pass_x,
                    uint32_t *n_launch_slots, uint64_t *launches, uint64_t *padded_cells) {
     const osw_shard &s = d.shard;
     const uint64_t N = s.n_seqs;
@@ -622,15 +632,45 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             // one warp per scheduler, so that they advance at the latency of a step rather than at a
             // quarter of the scheduler's issue rate.  (Threshold 1.5 measured: at a ratio of 1.15 the
             // express CTAs cost 4 %, at 1.9 they gain 6 %, at 3.5 and above 20-40 %.)
-            up.express_ctas = 0;
+            up.express_ctas = 0; up.all_express = 0;
+            uint32_t x_chunks = 0, x_ctas = 0;
             if (end > first && c->tune.express) {
-                const LaunchModel m(ps.G, ps.R, pd, (double)cols, d.n_sms);
+                const LaunchModel m(ps.G, ps.R, pd, (double)cols, d.n_sms, (double)(end - first));
                 const double longest = (double)chunk_cols(first);
                 if (longest * m.contended > c->tune.express_ratio * m.t_pipe) {
-                    const double cut = longest * m.alone / m.contended;      // shorter chunks finish in time anyway
-                    uint32_t n = 0;
-                    while (first + n < end && n < 64u * m.groups && (double)chunk_cols(first + n) > cut) ++n;
-                    up.express_ctas = std::min<uint32_t>(16, std::max<uint32_t>(1, (n + 4 * m.groups - 1) / (4 * m.groups)));
+                    if (pass_x && !d.streaming && passes.size() == 1 && (pass_x->G != ps.G || pass_x->R < ps.R) && c->tune.long_chunks != 0) {
+                        // Long-chunk launch: a step takes longer the more rows a lane holds (140 + 7 R cycles
+                        // for a warp alone on its scheduler), so the chunks whose walk would outlast the
+                        // launch go to a SECOND, concurrent launch of the same kernel with the widest array
+                        // (32 lanes x 8..16 rows) on a few SMs of their own, every CTA an express CTA, while
+                        // the geometry that suits the bulk (fewest padded rows) runs on the other SMs.
+                        // It takes the chunks that could not be walked among busy neighbours within the
+                        // launch's target time, on as many SMs as finish them in that time - unless that
+                        // needs more than 32 (a tiny database, where nearly every chunk is "long": measured
+                        // slower than the express CTAs).  Measured with it: 100 000 / 200 000 sequences x one
+                        // 144-residue query + 12 % / + 6 %, two short queries x 10 000 sequences + 4 %.
+                        const LaunchModel full(ps.G, ps.R, pd, (double)cols, d.n_sms);
+                        const LaunchModel mx(32, pass_x->R, pd, 0.0, d.n_sms);
+                        const double target = std::max(full.t_pipe, longest * mx.alone);
+                        double x_cols = 0;
+                        uint32_t n = 0;
+                        while (first + n < end && n < 4096u && (double)chunk_cols(first + n) * full.contended > target) { x_cols += (double)chunk_cols(first + n); ++n; }
+                        const double ctas = std::ceil(x_cols * mx.alone / target / 4.0);
+                        if (n && ctas <= 32.0) { x_chunks = n; x_ctas = (uint32_t)std::max(1.0, std::min(ctas, std::ceil(n / 4.0))); }
+                        if (c->tune.long_chunks > 0) {          // experiments: force the number of chunks of the long-chunk launch
+                            x_chunks = std::min<uint32_t>((uint32_t)c->tune.long_chunks, end - first);
+                            x_ctas = std::max<uint32_t>(1, std::min<uint32_t>(32, (x_chunks + 15) / 16));
+                        }
+                    }
+                    if (!x_chunks) {
+                        // Express CTAs inside the launch: the longest chunk groups get a scheduler each
+                        // (threshold 1.5 measured: at a ratio of 1.15 they cost 4 %, at 1.9 they gain 6 %, at
+                        // 3.5 and above 20-40 %).
+                        const double cut = longest * m.alone / m.contended;      // shorter chunks finish in time anyway
+                        uint32_t n = 0;
+                        while (first + n < end && n < 64u * m.groups && (double)chunk_cols(first + n) > cut) ++n;
+                        up.express_ctas = std::min<uint32_t>(16, std::max<uint32_t>(1, (n + 4 * m.groups - 1) / (4 * m.groups)));
+                    }
                 }
             }
             up.queries = d.d_queries; up.q_off = d.d_qoff; up.matrix = d.d_matrix;
@@ -638,11 +678,34 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             up.scores = d.d_scores; up.n_seqs = N;
             up.bound = d.d_bound; up.bound_col0 = bound_col0;
             up.gap_open_extend = go + ge; up.gap_extend = ge;
+            if (x_chunks) {
+                if (slot + 1 >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
+                // fork: the long-chunk launch starts when everything enqueued so far (uploads, clears) is done
+                CK(cudaEventRecord(d.ev_ready[0], d.st));
+                CK(cudaStreamWaitEvent(d.st_copy, d.ev_ready[0], 0));
+                U16Params xp = up;
+                xp.profile = d.d_profile_x; xp.first_table = d.d_first_table_x; xp.all_express = 1;
+                xp.chunk_first = first; xp.chunk_end = first + x_chunks;
+                xp.chunk_counter = d.d_counters + 1 + slot; xp.cycle_acc = nullptr;
+                ++slot;
+                int rcx = osw_launch_u16(xp, *pass_x, (int)x_ctas, d.st_copy);
+                if (rcx != OSW_OK) { cuda_fail(cudaGetLastError(), "long-chunk launch", __LINE__); return rcx; }
+                CK(cudaEventRecord(d.ev_free[0], d.st_copy));
+                *launches += 2;
+                uint64_t xc = 0;
+                for (uint32_t k = 0; k < x_chunks; ++k) xc += chunk_cols(first + k);
+                *padded_cells += (uint64_t)32 * pass_x->R * 2 * xc;
+                up.chunk_first = first + x_chunks;
+                cols -= xc;
+            }
             up.chunk_counter = d.d_counters + 1 + slot;
             up.cycle_acc = d.d_cycles + slot;
-            int rc2 = osw_launch_u16(up, ps, d.n_sms, d.st);
+            // (beside a long-chunk launch the scoring launch leaves it its SMs: both are resident at once,
+            // whichever the hardware places first - a full-width grid would make the other one wait)
+            int rc2 = osw_launch_u16(up, ps, d.n_sms - (int)x_ctas, d.st);
             if (rc2 != OSW_OK) { cuda_fail(cudaGetLastError(), "sw_u16 launch", __LINE__); return rc2; }
-            d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols, up.express_ctas, slot});
+            if (x_chunks) CK(cudaStreamWaitEvent(d.st, d.ev_free[0], 0));          // join
+            d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols, up.express_ctas, slot, x_chunks, x_ctas, x_chunks ? pass_x->R : 0});
             ++slot; *launches += 2;               // profile_build_kernel + sw_u16_kernel
             *padded_cells += (uint64_t)ps.G * ps.R * 2 * cols;
             return OSW_OK;
@@ -790,6 +853,8 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
                         osw_hit *hits, uint32_t *n_hits, int32_t *all_scores, osw_timing *timing) {
     const double t_wall0 = now_ms();
     std::vector<OswPass> passes;
+    OswPass plan_x;
+    bool have_x = false;
     if (c->kernel_mask & OSW_K_U16) {
         std::vector<uint32_t> q_len((size_t)nq);
         for (int q = 0; q < nq; ++q) q_len[q] = q_off[q + 1] - q_off[q];
@@ -797,6 +862,13 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
         const int mode = (c->kernel_mask & OSW_K_PAIR_DB) ? OSW_PLAN_PAIR_DB : (c->kernel_mask & OSW_K_TWO_TRACK) ? OSW_PLAN_TWO_TRACK : OSW_PLAN_AUTO;
         int n_pass = osw_plan_passes_ex(q_len.data(), nq, passes.data(), MAX_PASSES, mode, 4, c->tune.rmax);
         if (n_pass < 0) { snprintf(g_err, sizeof g_err, "the queries need more than %d passes", MAX_PASSES); return OSW_E_ARG; }
+        // A single-pass plan that also fits 32 lanes x <= 16 rows can hand its longest chunks to a
+        // launch of that geometry (same halves, same directory; the launcher decides per launch).
+        if (n_pass == 1) {
+            OswPass alt[2];
+            if (osw_plan_passes_ex(q_len.data(), nq, alt, 2, passes[0].pair_db ? OSW_PLAN_PAIR_DB : OSW_PLAN_TWO_TRACK, 32, 16) == 1 &&
+                alt[0].R <= 16 && alt[0].pair_db == passes[0].pair_db) { plan_x = alt[0]; have_x = true; }
+        }
         if (n_pass == 1 && passes[0].G < 32) {
             // The planner picked the geometry with the fewest padded rows.  That is the fastest one
             // when the launch is bound by the DPX pipe; on a small database the launch lasts as long
@@ -831,7 +903,7 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
     // ---- phase 1: first stage on every GPU ------------------------------------------------
     for (int i = 0; i < c->n_dev; ++i) {
         int rc = enqueue_search(c, c->devs[i], queries, q_off, nq, matrix, go, ge, (uint32_t)top_r,
-                                all_scores != nullptr, passes, &slots[i], &launches, &padded);
+                                all_scores != nullptr, passes, have_x ? &plan_x : nullptr, &slots[i], &launches, &padded);
         if (rc != OSW_OK) return rc;
     }
     const double t_h2d = now_ms();
@@ -943,8 +1015,8 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
                 const LaunchRecord &lr = d.trace[k];
                 const unsigned long long cyc = std::max<unsigned long long>(d.h_cycles[lr.slot], 1);
                 const double cells = 2.0 * lr.G * lr.R * (double)lr.cols;
-                fprintf(stderr, "osw trace: launch %u/%zu G=%d R=%d in=%d out=%d pairdb=%d express=%u chunks [%u,%u)  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
-                        k + 1, d.trace.size(), lr.G, lr.R, lr.has_in, lr.has_out, lr.pair_db, lr.express, lr.first, lr.end,
+                fprintf(stderr, "osw trace: launch %u/%zu G=%d R=%d in=%d out=%d pairdb=%d express=%u long[R=%d chunks=%u ctas=%u] chunks [%u,%u)  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
+                        k + 1, d.trace.size(), lr.G, lr.R, lr.has_in, lr.has_out, lr.pair_db, lr.express, lr.x_R, lr.x_chunks, lr.x_ctas, lr.first, lr.end,
                         cyc / d.n_sms, cells / (double)cyc);
             }
         }

@@ -82,11 +82,13 @@ struct U16Params {
     uint32_t        *chunk_counter;
     uint32_t         static_first;   // deal every warp's first chunk statically, through the table (set by the launcher: few chunks per warp)
     uint32_t         express_ctas;   // CTAs that give the longest chunks a scheduler each (0 = none)
+    uint32_t         all_express;    // the launch consists of express CTAs only (the long-chunk launch of a small database)
     uint32_t        *first_table;    // [CTAs x warps] first chunk group of every warp (filled by profile_build_kernel), >= 148 * 16 entries
     uint32_t         dyn_base;       // first group handed out by the counter (set by the launcher)
     unsigned long long *cycle_acc;   // sum over CTAs of their elapsed clock64 cycles (one CTA per SM), or nullptr
 };
-int osw_launch_u16(const U16Params &p, const OswPass &pass, int n_sms, cudaStream_t st);
+// n_ctas CTAs (normally one per SM; a long-chunk launch and the launch beside it share the SMs).
+int osw_launch_u16(const U16Params &p, const OswPass &pass, int n_ctas, cudaStream_t st);
 
 // ---- device top-r (topr.cu) --------------------------------------------------------------
 struct TopRWork {            // per-device scratch, sized for nq_max queries

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) profile_build_kernel(const KArgs a) {
     //    short chunks (measured + 2..6 % there, - 2.4 % on a large database, which uses the counter);
     //  * every other warp starts at the counter like later fetches do (entry = NO_GROUP + 1).
     if (a.p.first_table && blockIdx.x == 0) {
-        const uint32_t K = min(a.p.express_ctas, a.n_ctas - 1);
+        const uint32_t K = a.p.all_express ? a.n_ctas : min(a.p.express_ctas, a.n_ctas - 1);
         for (uint32_t i = threadIdx.x; i < a.n_ctas * a.warps; i += 256) {
             const uint32_t b = i / a.warps, w = i % a.warps;
             uint32_t g;
@@ -484,15 +484,11 @@ sw_u16_kernel(const KArgs a) {
 
 template <int G, int R, int THREADS, bool PD, bool DEAL>
 int launch_kernel(const KArgs &k, int n_sms, size_t smem, cudaStream_t st) {
-    static bool configured[64] = {};          // the attribute is per device
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return OSW_E_CUDA;
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-        if (smem > 227 * 1024) return OSW_E_ARG;
-        if (cudaFuncSetAttribute(sw_u16_kernel<G, R, THREADS, PD, DEAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return OSW_E_CUDA;
-        if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
+    // (set on every launch: the attribute is per device and per function, the call costs about a
+    // microsecond, and a "configured" flag here would be shared state between host threads)
+    if (smem > 227 * 1024) return OSW_E_ARG;
+    if (cudaFuncSetAttribute(sw_u16_kernel<G, R, THREADS, PD, DEAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return OSW_E_CUDA;
     profile_build_kernel<G, R, PD><<<32, 256, 0, st>>>(k);
     sw_u16_kernel<G, R, THREADS, PD, DEAL><<<n_sms, THREADS, smem, st>>>(k);
     return cudaGetLastError() == cudaSuccess ? OSW_OK : OSW_E_CUDA;
@@ -506,8 +502,14 @@ int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
     constexpr uint32_t WARPS = THREADS / 32;
     const uint32_t slots = (uint32_t)n_sms * WARPS * (32 / G);          // chunks in flight
     const bool few_chunks = a.p.chunk_end - a.p.chunk_first < 12 * slots;
-    const uint32_t K = std::min<uint32_t>(a.p.express_ctas, (uint32_t)n_sms - 1);
     k.n_ctas = (uint32_t)n_sms; k.warps = WARPS;
+    if (a.p.all_express) {          // a long-chunk launch: every CTA gives four chunks a scheduler each, the rest from the counter
+        k.p.express_ctas = (uint32_t)n_sms;
+        k.p.static_first = 0u;
+        k.p.dyn_base = 4u * (uint32_t)n_sms;
+        return launch_kernel<G, R, THREADS, PD, true>(k, n_sms, smem, st);
+    }
+    const uint32_t K = std::min<uint32_t>(a.p.express_ctas, (uint32_t)n_sms - 1);
     if (K || few_chunks) {          // express CTAs and / or a static first deal: through the table
         k.p.express_ctas = K;
         k.p.static_first = few_chunks ? 1u : 0u;

@@ -196,13 +196,7 @@ int osw_topr_select(const int32_t *scores, const uint32_t *canon, uint64_t n_seq
         rd.shift[rd.n++] = 8 * byte;
     }
     if (n_seqs <= OSW_TOPR_SMALL_MAX) {
-        static bool configured[64] = {};          // the attribute is per device; set once (idempotent, so a race is harmless)
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64 || !configured[dev]) {
-            cudaFuncSetAttribute(topr_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OSW_TOPR_SMALL_MAX * 8);
-            if (dev >= 0 && dev < 64) configured[dev] = true;
-        }
+        cudaFuncSetAttribute(topr_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OSW_TOPR_SMALL_MAX * 8);
         topr_small_kernel<<<nq, SMALL_THREADS, (size_t)n_seqs * 8, st>>>(scores, canon, (uint32_t)n_seqs, r, rd, w, flags ? *flags : none);
         return 1;
     }

@@ -71,7 +71,40 @@ def append_records(path, recs):
                 f.write(s[k:k + 60] + "\n")
 
 
+def case_g4(w):
+    """G4: scores beyond 16 bits - the reference's own 32-bit stage (HybridSearch.c:1046-1134) pins
+    what the GPU's 32-bit re-score returns.  Tryptophan-rich queries and database sequences under
+    PAM30 9/1 (W/W = 13): exact and mutated copies, all-W runs, and pairs on both sides of the packed
+    16-bit kernel's flag threshold (65 504 - bias)."""
+    rng = np.random.default_rng(44)
+    aa = "ACDEFGHIKLMNPQRSTVWY"
+
+    def rand(n):
+        return "".join(aa[i] for i in rng.integers(0, 20, size=n))
+
+    def w_rich(n, frac):
+        return "".join("W" if x < frac else aa[i] for x, i in zip(rng.random(n), rng.integers(0, 20, size=n)))
+
+    q_rich = w_rich(5400, 0.93)
+    q_all = "W" * 5300
+    queries = [("q_rand144", rand(144)), ("q_allW5300", q_all), ("q_rich5400", q_rich), ("q_rand3000", rand(3000))]
+    open(w + "/q4.fasta", "w").close()
+    append_records(w + "/q4.fasta", queries)
+    sh(SYNTH, "db", "-n", "600", "-mu", "4.8", "-sigma", "0.6", "-seed", "23", "-o", w + "/db4.fasta")
+    recs = [("copy_rich", q_rich), ("rich_indel", q_rich[:2600] + rand(7) + q_rich[2600:]), ("rich_other", w_rich(6000, 0.9)),
+            ("copy_rand3000", queries[3][1])]
+    recs += [("allW_%d" % n, "W" * n) for n in (5020, 5030, 5035, 5036, 5037, 5040, 5100, 5300, 7000, 20000)]
+    recs += [("allW_rand_%d" % k, "W" * int(n)) for k, n in enumerate(rng.integers(4800, 9000, size=12))]
+    append_records(w + "/db4.fasta", recs)
+    run_case("g4_wide", w + "/db4.fasta", w + "/q4.fasta", [("pam30", 9, 1), ("blosum62", 10, 2)], 15, 0.3)
+
+
 def main():
+    if "--only-g4" in sys.argv:
+        w = tempfile.mkdtemp()
+        case_g4(w)
+        shutil.rmtree(w)
+        return
     if not os.path.exists(REF):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
     if not os.path.exists(SYNTH):
@@ -98,6 +131,7 @@ def main():
     run_case("g3_kat", w + "/db3.fasta", w + "/q3.fasta",
              [("blosum62", 10, 2), ("blosum50", 10, 2), ("pam30", 9, 1), ("blosum45", 14, 2),
               ("blosum80", 10, 2), ("blosum90", 10, 2), ("pam70", 10, 1), ("pam250", 12, 2)], 8, 0.3)
+    case_g4(w)
     shutil.rmtree(w)
 
 

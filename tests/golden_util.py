@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["g1_random", "g2_overflow", "g3_kat"]
+CASES = ["g1_random", "g2_overflow", "g3_kat", "g4_wide"]
 
 
 def load_case(name):

@@ -64,9 +64,13 @@ def test_golden_cases(searcher, name, mask):
             got = [[s, db.titles[i]] for s, i in hits[qi]]
             assert got == h["top"], (name, run["matrix"], qi)
         if mask != capi.OSW_K_I32:
-            # the reference needed its 16- and 32-bit stages here (scores up to 44 783 > 32 767);
-            # the biased unsigned 16-bit kernel holds them, so nothing is re-scored
-            assert tm["rescored_pairs"] == 0
+            # g2: the reference needed its 16- and 32-bit stages (scores up to 44 783 > 32 767); the biased
+            # unsigned 16-bit kernel holds them, so nothing is re-scored.  g4 (up to 68 900): exactly the
+            # pairs at or above the flag threshold go to the GPU's 32-bit stage, and what comes back is
+            # what the reference's own 32-bit stage (HybridSearch.c:1046-1134) computed.
+            bias = run["gap_open"] + 2 * run["gap_extend"] + 32
+            assert tm["rescored_pairs"] == int((run["score_matrix"] + bias >= 65504).sum())
+            assert name != "g4_wide" or run["matrix"] != "pam30" or tm["rescored_pairs"] >= 20
 
 
 MODES = {"auto": capi.OSW_K_DEFAULT, "two_track": capi.OSW_K_DEFAULT | capi.OSW_K_TWO_TRACK,
@@ -495,6 +499,31 @@ def test_forced_group_widths(built, monkeypatch, min_g):
             q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in lens])
             for mode in MODES.values():
                 check(s, db, q, "blosum62", 10, 2, 10, mask=mode)
+
+
+@pytest.mark.parametrize("n_long", ["3", "100000"])
+def test_long_chunk_launch(built, monkeypatch, n_long):
+    """Small databases: the longest chunks of a chain-bound single-pass launch go to a second, concurrent
+    launch with the widest array (32 lanes x 8..16 rows, every CTA an express CTA) - forced here to take a
+    few chunks / every chunk: one or several queries, both uses of the packed halves, empty and long
+    sequences, overflow, tiny chunks."""
+    monkeypatch.setenv("OSW_LONG_CHUNKS", n_long)
+    monkeypatch.setenv("OSW_EXPRESS_RATIO", "0")            # every launch counts as chain-bound
+    rng = np.random.default_rng(77 + int(n_long))
+    W = np.uint8(19)
+    seqs = rand_seqs(rng, 900, 0, 500) + [AA[rng.integers(0, 20, size=n)] for n in (2500, 9000, 65535)] + [np.full(7000, W, dtype=np.uint8)]
+    db = make_db(seqs)
+    with ob.Searcher(1) as s:
+        s.load_db(db)
+        for lens in ([144], [30], [90, 100], [33, 150, 7, 61], [400], [500, 480], [256, 255, 1], [97] * 9):
+            q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in lens])
+            for mode in MODES.values():
+                check(s, db, q, "blosum62", 10, 2, 10, mask=mode)
+        q = ob.Queries.from_list([np.full(400, W, dtype=np.uint8), AA[rng.integers(0, 20, size=300)]])
+        for mode in MODES.values():
+            check(s, db, q, "pam30", 9, 1, 10, mask=mode)
+        s.load_db(db, max_chunk_residues=64)
+        check(s, db, ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (144, 222)]), "blosum62", 10, 2, 10)
 
 
 def test_many_tiny_queries(built):
