@@ -27,7 +27,7 @@ namespace {
 constexpr uint32_t MAX_LAUNCH_SLOTS = 4096;
 constexpr uint32_t FLAG_CAPACITY_MIN = 1u << 16;
 
-struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; uint32_t express; uint32_t slot; uint32_t x_chunks, x_ctas; int x_R; };
+struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; uint32_t express; uint32_t slot; uint32_t x_chunks, x_ctas; int x_R; uint32_t pipe_chunks; };
 
 struct DevState {
     int dev = -1, n_sms = 0;
@@ -59,6 +59,10 @@ struct DevState {
     unsigned char *d_profile = nullptr;        // the current pass's profile table image
     unsigned char *d_profile_x = nullptr;      // ... of a long-chunk launch beside it
     uint32_t *d_first_table_x = nullptr;
+    // pipelined passes over the longest chunks: one stream, profile image, deal table and progress row per pass
+    std::vector<cudaStream_t> pipe_st;
+    std::vector<cudaEvent_t> pipe_ev;
+    unsigned char *d_profile_pipe = nullptr; uint32_t *d_first_table_pipe = nullptr; uint32_t *d_progress = nullptr;
     uint32_t *d_first_table = nullptr;         // the current pass's first-chunk deal (CTAs x warps)
     uint2 *d_pairs = nullptr; uint32_t pairs_cap = 0;
     uint32_t *d_counters = nullptr;            // [0] flagged count, [1..] chunk counters per launch
@@ -140,6 +144,7 @@ struct Tunables {
     int      force_g = 0;               // OSW_MIN_G: force a group width for single-pass plans
     int      rmax = 0;                  // OSW_RMAX: rows per lane of the full-height passes (0 = default)
     int      long_chunks = -1;          // OSW_LONG_CHUNKS: force the number of chunks of the long-chunk launch (0 = never)
+    int      pipe_chunks = -1;          // OSW_PIPE_CHUNKS: force the number of chunks whose passes are pipelined (0 = never)
     bool     trace = false;             // OSW_TRACE: per-launch report on stderr
     void read() {
         if (const char *e = getenv("OSW_CHUNK_COLS")) { const int v = atoi(e); if (v >= 64) chunk_cols = (uint32_t)v; }
@@ -151,6 +156,7 @@ struct Tunables {
         if (const char *e = getenv("OSW_MIN_G")) force_g = atoi(e);
         if (const char *e = getenv("OSW_RMAX")) rmax = atoi(e);
         if (const char *e = getenv("OSW_LONG_CHUNKS")) long_chunks = atoi(e);
+        if (const char *e = getenv("OSW_PIPE_CHUNKS")) pipe_chunks = atoi(e);
         trace = getenv("OSW_TRACE") != nullptr;
     }
 };
@@ -281,6 +287,9 @@ extern "C" void osw_free(osw_ctx *c) {
         for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
         for (int k = 0; k < 2; ++k) { if (d.ev_ready[k]) cudaEventDestroy(d.ev_ready[k]); if (d.ev_free[k]) cudaEventDestroy(d.ev_free[k]); }
         if (d.st_copy) cudaStreamDestroy(d.st_copy);
+        for (cudaStream_t ps : d.pipe_st) cudaStreamDestroy(ps);
+        for (cudaEvent_t pe : d.pipe_ev) cudaEventDestroy(pe);
+        cudaFree(d.d_profile_pipe); cudaFree(d.d_first_table_pipe); cudaFree(d.d_progress);
         cudaFree(d.d_stage); cudaFree(d.d_task_off);
         if (d.h_stage) cudaFreeHost(d.h_stage);
         if (d.h_task_off) cudaFreeHost(d.h_task_off);
@@ -613,6 +622,8 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             const uint64_t al = pd ? 64 : OSW_CHUNK_ALIGN;
             return chunk_begin(k) + (chunk_cols(k) + al - 1) / al * al;
         };
+        constexpr uint32_t PIPE_MAX_PASSES = 64, PIPE_MAX_CHUNKS = 16;
+        uint32_t reserved_ctas = 0;           // SMs left to the pipelined launches of the longest chunks
         auto launch = [&](const OswPass &ps, uint32_t first, uint32_t end) -> int {
             if (slot >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
             U16Params up;
@@ -632,9 +643,9 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             // one warp per scheduler, so that they advance at the latency of a step rather than at a
             // quarter of the scheduler's issue rate.  (Threshold 1.5 measured: at a ratio of 1.15 the
             // express CTAs cost 4 %, at 1.9 they gain 6 %, at 3.5 and above 20-40 %.)
-            up.express_ctas = 0; up.all_express = 0;
+            up.express_ctas = 0; up.all_express = 0; up.progress_in = nullptr; up.progress_out = nullptr;
             uint32_t x_chunks = 0, x_ctas = 0;
-            if (end > first && c->tune.express) {
+            if (end > first && c->tune.express && !reserved_ctas) {
                 const LaunchModel m(ps.G, ps.R, pd, (double)cols, d.n_sms, (double)(end - first));
                 const double longest = (double)chunk_cols(first);
                 if (longest * m.contended > c->tune.express_ratio * m.t_pipe) {
@@ -702,10 +713,10 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             up.cycle_acc = d.d_cycles + slot;
             // (beside a long-chunk launch the scoring launch leaves it its SMs: both are resident at once,
             // whichever the hardware places first - a full-width grid would make the other one wait)
-            int rc2 = osw_launch_u16(up, ps, d.n_sms - (int)x_ctas, d.st);
+            int rc2 = osw_launch_u16(up, ps, d.n_sms - (int)x_ctas - (int)reserved_ctas, d.st);
             if (rc2 != OSW_OK) { cuda_fail(cudaGetLastError(), "sw_u16 launch", __LINE__); return rc2; }
             if (x_chunks) CK(cudaStreamWaitEvent(d.st, d.ev_free[0], 0));          // join
-            d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols, up.express_ctas, slot, x_chunks, x_ctas, x_chunks ? pass_x->R : 0});
+            d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols, up.express_ctas, slot, x_chunks, x_ctas, x_chunks ? pass_x->R : 0, 0u});
             ++slot; *launches += 2;               // profile_build_kernel + sw_u16_kernel
             *padded_cells += (uint64_t)ps.G * ps.R * 2 * cols;
             return OSW_OK;
@@ -744,8 +755,82 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
                         win_ptr = d.d_win[w]; win_col0 = seg_col0;
                     }
                 }
-                for (const OswPass &ps : passes)
-                    if ((rc = launch(ps, seg_first, seg_end)) != OSW_OK) return rc;
+                // Pipelined passes over the LONGEST chunks.  Every pass walks a chunk column by column, so a
+                // titin-length sequence costs n_passes sequential walks (BASELINE.json config 5 on eight
+                // GPUs: 17 x 14 ms of a 177 ms search were 337 ms).  But pass p + 1 needs, at column j, only
+                // what pass p has produced up to column j: the walks can run at the same time, a few dozen
+                // columns apart, each pass on an SM of its own with its own profile table, handing the
+                // bottom row over through the same in-place buffer under per-chunk progress counters.
+                uint32_t n_pipe = 0;
+                if (seg_first == 0 && seg_end == n_dir && bounded && !d.streaming && c->tune.express && c->tune.pipe_chunks != 0 &&
+                    passes.size() >= 2 && passes.size() <= PIPE_MAX_PASSES) {
+                    double t_total = 0, step_sum = 0;
+                    bool all32 = true;
+                    for (const OswPass &ps : passes) {
+                        const LaunchModel m(ps.G, ps.R, pd, (double)(pd ? s.pair_cols : s.n_residues), d.n_sms);
+                        t_total += m.t_pipe; step_sum += m.contended; all32 &= ps.G == 32;
+                    }
+                    while (all32 && n_pipe < PIPE_MAX_CHUNKS && n_pipe < n_dir && (double)chunk_cols(n_pipe) * step_sum > 1.5 * t_total) ++n_pipe;
+                    if (c->tune.pipe_chunks > 0 && all32) n_pipe = std::min<uint32_t>(std::min<uint32_t>((uint32_t)c->tune.pipe_chunks, PIPE_MAX_CHUNKS), n_dir);
+                    const uint32_t ctas_per_pass = (n_pipe + 3) / 4;
+                    if (ctas_per_pass * passes.size() > (size_t)d.n_sms / 2) n_pipe = 0;
+                    if (n_pipe) {
+                        const size_t np = passes.size();
+                        if (!d.d_profile_pipe) {
+                            CK(cudaMalloc(&d.d_profile_pipe, (size_t)PIPE_MAX_PASSES * OSW_PROFILE_BYTES));
+                            CK(cudaMalloc(&d.d_first_table_pipe, (size_t)PIPE_MAX_PASSES * 1024 * sizeof(uint32_t)));
+                            CK(cudaMalloc(&d.d_progress, (size_t)PIPE_MAX_PASSES * PIPE_MAX_CHUNKS * sizeof(uint32_t)));
+                        }
+                        while (d.pipe_st.size() < np) {
+                            cudaStream_t st2; cudaEvent_t ev2;
+                            CK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+                            d.pipe_st.push_back(st2);
+                            CK(cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming));
+                            d.pipe_ev.push_back(ev2);
+                        }
+                        CK(cudaMemsetAsync(d.d_progress, 0, (size_t)PIPE_MAX_PASSES * PIPE_MAX_CHUNKS * sizeof(uint32_t), d.st));
+                        CK(cudaEventRecord(d.ev_ready[0], d.st));                  // fork
+                        uint64_t pipe_cols = 0;
+                        for (uint32_t k = 0; k < n_pipe; ++k) pipe_cols += chunk_cols(k);
+                        for (size_t pi = 0; pi < np; ++pi) {
+                            if (slot >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
+                            const OswPass &ps = passes[pi];
+                            CK(cudaStreamWaitEvent(d.pipe_st[pi], d.ev_ready[0], 0));
+                            U16Params xp;
+                            xp.stream = d.d_stream; xp.pair_stream = d.d_pair; xp.stream_col0 = 0;
+                            xp.chunks = pd ? d.d_pair_chunks : d.d_chunks;
+                            xp.chunk_first = 0; xp.chunk_end = n_pipe; xp.static_first = 0;
+                            xp.express_ctas = 0; xp.all_express = 1;
+                            xp.queries = d.d_queries; xp.q_off = d.d_qoff; xp.matrix = d.d_matrix;
+                            xp.profile = d.d_profile_pipe + pi * OSW_PROFILE_BYTES; xp.first_table = d.d_first_table_pipe + pi * 1024; xp.dyn_base = 0;
+                            xp.scores = d.d_scores; xp.n_seqs = N;
+                            xp.bound = d.d_bound; xp.bound_col0 = bound_col0;
+                            xp.gap_open_extend = go + ge; xp.gap_extend = ge;
+                            xp.chunk_counter = d.d_counters + 1 + slot; xp.cycle_acc = nullptr;
+                            xp.progress_in = pi ? d.d_progress + (pi - 1) * PIPE_MAX_CHUNKS : nullptr;
+                            xp.progress_out = pi + 1 < np ? d.d_progress + pi * PIPE_MAX_CHUNKS : nullptr;
+                            ++slot;
+                            int rcx = osw_launch_u16(xp, ps, (int)ctas_per_pass, d.pipe_st[pi]);
+                            if (rcx != OSW_OK) { cuda_fail(cudaGetLastError(), "pipelined launch", __LINE__); return rcx; }
+                            CK(cudaEventRecord(d.pipe_ev[pi], d.pipe_st[pi]));
+                            *launches += 2;
+                            *padded_cells += (uint64_t)ps.G * ps.R * 2 * pipe_cols;
+                            d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, 0u, n_pipe, pipe_cols, ctas_per_pass, slot - 1, 0u, 0u, 0, n_pipe});
+                        }
+                        reserved_ctas = ctas_per_pass * (uint32_t)np;
+                    }
+                }
+                for (const OswPass &ps : passes) {
+                    if ((rc = launch(ps, seg_first + n_pipe, seg_end)) != OSW_OK) return rc;
+                    // (only the first pass leaves the pipelined launches their SMs, so that they are resident
+                    // at once; they are done after a pass or two, and the later passes run at full width - a
+                    // CTA that finds no free SM yet simply starts when a pipelined one has left)
+                    reserved_ctas = 0;
+                }
+                if (n_pipe) {
+                    for (size_t pi = 0; pi < passes.size(); ++pi) CK(cudaStreamWaitEvent(d.st, d.pipe_ev[pi], 0));      // join
+                    reserved_ctas = 0;
+                }
                 if (d.streaming) CK(cudaEventRecord(d.ev_free[seg_no & 1], d.st));
                 seg_first = seg_end; ++seg_no;
             }
@@ -1015,8 +1100,8 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
                 const LaunchRecord &lr = d.trace[k];
                 const unsigned long long cyc = std::max<unsigned long long>(d.h_cycles[lr.slot], 1);
                 const double cells = 2.0 * lr.G * lr.R * (double)lr.cols;
-                fprintf(stderr, "osw trace: launch %u/%zu G=%d R=%d in=%d out=%d pairdb=%d express=%u long[R=%d chunks=%u ctas=%u] chunks [%u,%u)  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
-                        k + 1, d.trace.size(), lr.G, lr.R, lr.has_in, lr.has_out, lr.pair_db, lr.express, lr.x_R, lr.x_chunks, lr.x_ctas, lr.first, lr.end,
+                fprintf(stderr, "osw trace: launch %u/%zu G=%d R=%d in=%d out=%d pairdb=%d express=%u long[R=%d chunks=%u ctas=%u] pipelined=%u chunks [%u,%u)  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
+                        k + 1, d.trace.size(), lr.G, lr.R, lr.has_in, lr.has_out, lr.pair_db, lr.express, lr.x_R, lr.x_chunks, lr.x_ctas, lr.pipe_chunks, lr.first, lr.end,
                         cyc / d.n_sms, cells / (double)cyc);
             }
         }

@@ -86,6 +86,10 @@ struct U16Params {
     uint32_t        *first_table;    // [CTAs x warps] first chunk group of every warp (filled by profile_build_kernel), >= 148 * 16 entries
     uint32_t         dyn_base;       // first group handed out by the counter (set by the launcher)
     unsigned long long *cycle_acc;   // sum over CTAs of their elapsed clock64 cycles (one CTA per SM), or nullptr
+    // Pipelined passes over the longest chunks (api.cu): the launches of consecutive passes run at the same
+    // time on different SMs; progress_out[k] = columns of chunk chunk_first + k whose bottom row this pass has
+    // written, progress_in[k] = the same of the pass before, which this launch waits for block by block.
+    uint32_t        *progress_in, *progress_out;
 };
 // n_ctas CTAs (normally one per SM; a long-chunk launch and the launch beside it share the SMs).
 int osw_launch_u16(const U16Params &p, const OswPass &pass, int n_ctas, cudaStream_t st);

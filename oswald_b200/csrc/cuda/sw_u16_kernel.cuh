@@ -209,7 +209,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 // A template flag rather than a run-time test: the R = 40 row sweep uses every register it can
 // get, and even a loop-carried flag in the fetch path changed the schedule ptxas finds for the
 // sweep (- 0.8..1.7 % at config 2, measured against the previous build on the same box).
-template <int G, int R, int THREADS, bool PD, bool DEAL>
+// PIPE = pipelined passes: the launch runs beside the launches of the passes before and after it, each on
+// SMs of its own, all walking the same (longest) chunks a few dozen columns apart.  Before a warp reads the
+// bottom row of a 32-column block it waits until the pass before has written it (progress_in), and after it
+// has flushed its own bottom row of a block it says so (progress_out).  Only the G = 32, DEAL variants exist.
+__device__ __forceinline__ void wait_progress(const uint32_t *counter, uint32_t need) {
+    if ((threadIdx.x & 31) == 0) {
+        uint32_t have;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(counter) : "memory"); } while (have < need);
+    }
+    __syncwarp();
+}
+
+template <int G, int R, int THREADS, bool PD, bool DEAL, bool PIPE = false>
 __global__ void __launch_bounds__(THREADS, 1)
 sw_u16_kernel(const KArgs a) {
     constexpr int WARPS = THREADS / 32;
@@ -330,6 +342,11 @@ sw_u16_kernel(const KArgs a) {
                 sts128(dst + e * 16, make_uint4(pre_bnd.x, pre_bnd.y, B2, w));
             }
         };
+        // (waiting and reporting do not depend on whether THIS pass reads or writes a bottom row: the buffer is
+        // updated in place, so no pass may overtake the one before it)
+        const uint32_t *prog_in = PIPE && p.progress_in && have ? p.progress_in + (ci - p.chunk_first) : nullptr;
+        uint32_t *prog_out = PIPE && p.progress_out && have ? p.progress_out + (ci - p.chunk_first) : nullptr;
+        if (PIPE && prog_in) wait_progress(prog_in, min(32u, n_cols));
         prefetch(0);
         commit(0);
 
@@ -346,6 +363,7 @@ sw_u16_kernel(const KArgs a) {
         __syncwarp();
 
         for (uint32_t blk = 0; blk < n_blocks; ++blk) {
+            if (PIPE && prog_in) wait_progress(prog_in, min(32u * (blk + 2), n_cols));
             prefetch(blk + 1);
 #pragma unroll 1
             for (uint32_t i = 0; i < 32; ++i) {
@@ -475,6 +493,13 @@ sw_u16_kernel(const KArgs a) {
                 const uint32_t col = blk * 32 + lane - (NC * G - 1);
                 if (col < cols_padded) __stcg(out_base + col, lds64(oring_base + lane * 8));
             }
+            if (PIPE && prog_out) {              // the columns this block finished (and their bottom row) are done: tell the next pass
+                __threadfence();
+                __syncwarp();
+                const uint32_t done = blk * 32 + 32;
+                if (lane == 0 && done > (uint32_t)(NC * G - 1))
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(prog_out), "r"(blk + 1 == n_blocks ? 0xffffffffu : done - (NC * G - 1)) : "memory");
+            }
             commit(blk + 1);
             __syncwarp();
         }
@@ -482,15 +507,15 @@ sw_u16_kernel(const KArgs a) {
     if (p.cycle_acc && threadIdx.x == 0) atomicAdd(p.cycle_acc, (unsigned long long)(clock64() - clk0));
 }
 
-template <int G, int R, int THREADS, bool PD, bool DEAL>
+template <int G, int R, int THREADS, bool PD, bool DEAL, bool PIPE = false>
 int launch_kernel(const KArgs &k, int n_sms, size_t smem, cudaStream_t st) {
     // (set on every launch: the attribute is per device and per function, the call costs about a
     // microsecond, and a "configured" flag here would be shared state between host threads)
     if (smem > 227 * 1024) return OSW_E_ARG;
-    if (cudaFuncSetAttribute(sw_u16_kernel<G, R, THREADS, PD, DEAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(sw_u16_kernel<G, R, THREADS, PD, DEAL, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return OSW_E_CUDA;
     profile_build_kernel<G, R, PD><<<32, 256, 0, st>>>(k);
-    sw_u16_kernel<G, R, THREADS, PD, DEAL><<<n_sms, THREADS, smem, st>>>(k);
+    sw_u16_kernel<G, R, THREADS, PD, DEAL, PIPE><<<n_sms, THREADS, smem, st>>>(k);
     return cudaGetLastError() == cudaSuccess ? OSW_OK : OSW_E_CUDA;
 }
 
@@ -507,6 +532,10 @@ int launch_threads(const KArgs &a, int n_sms, cudaStream_t st) {
         k.p.express_ctas = (uint32_t)n_sms;
         k.p.static_first = 0u;
         k.p.dyn_base = 4u * (uint32_t)n_sms;
+        if (a.p.progress_in || a.p.progress_out) {
+            if constexpr (G == 32) return launch_kernel<G, R, THREADS, PD, true, true>(k, n_sms, smem, st);
+            else return OSW_E_ARG;
+        }
         return launch_kernel<G, R, THREADS, PD, true>(k, n_sms, smem, st);
     }
     const uint32_t K = std::min<uint32_t>(a.p.express_ctas, (uint32_t)n_sms - 1);

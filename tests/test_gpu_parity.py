@@ -429,6 +429,7 @@ def test_cli_two_gpus_same_report(built, tmp_path):
 
 def test_segmented_bottom_rows(built, monkeypatch):
     """Several passes with a bottom-row buffer that holds only a few chunks at a time."""
+    monkeypatch.setenv("OSW_PIPE_CHUNKS", "0")                  # (launch counts below: without the pipelined launches)
     rng = np.random.default_rng(88)
     seqs = rand_seqs(rng, 1500, 1, 400) + [AA[rng.integers(0, 20, size=n)] for n in (3000, 70000)]
     q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (1500, 2900, 1400)])
@@ -524,6 +525,31 @@ def test_long_chunk_launch(built, monkeypatch, n_long):
             check(s, db, q, "pam30", 9, 1, 10, mask=mode)
         s.load_db(db, max_chunk_residues=64)
         check(s, db, ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (144, 222)]), "blosum62", 10, 2, 10)
+
+
+@pytest.mark.parametrize("n_pipe", ["1", "5", "16"])
+def test_pipelined_passes_over_the_longest_chunks(built, monkeypatch, n_pipe):
+    """Several passes, the longest chunks walked by all passes at once (each pass on SMs of its own, a few
+    dozen columns apart, bottom rows handed over in place under progress counters): two-track and
+    pair-database plans, passes of different heights, passes that do and do not continue a query, titin-length
+    and ordinary chunks, overflow."""
+    monkeypatch.setenv("OSW_PIPE_CHUNKS", n_pipe)
+    rng = np.random.default_rng(300 + int(n_pipe))
+    W = np.uint8(19)
+    seqs = rand_seqs(rng, 1200, 0, 400) + [AA[rng.integers(0, 20, size=n)] for n in (3000, 20000, 40000, 65535)] + [np.full(8000, W, dtype=np.uint8)]
+    q_sets = [[1500, 2900, 1400], [3005], [5478, 144], [1280, 1280, 1280, 1280], [2560, 100, 100, 2000], [1281, 1279, 35, 2600, 7]]
+    db = make_db(seqs)
+    with ob.Searcher(1) as s:
+        s.load_db(db, max_chunk_residues=2048)
+        for lens in q_sets:
+            q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in lens])
+            seqs_q = q.query(q.n - 1)
+            want = oracle_scores(q, db, "blosum62", 10, 2)
+            for mode in MODES.values():
+                tm = check(s, db, q, "blosum62", 10, 2, 10, mask=mode, want=want)
+        q = ob.Queries.from_list([np.full(5300, W, dtype=np.uint8), AA[rng.integers(0, 20, size=1400)]])        # 68 900 > 16 bits
+        tm = check(s, db, q, "pam30", 9, 1, 10)
+        assert tm["rescored_pairs"] >= 1
 
 
 def test_many_tiny_queries(built):

@@ -23,10 +23,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden", "kernel_schedule.json")
 # the instances the headline workload and the single-query path run at full size
 KERNELS = {
-    "two_track_G32_R40": "_ZN7osw_u1613sw_u16_kernelILi32ELi40ELi384ELb0ELb0EEEvNS_5KArgsE",
-    "two_track_G32_R20": "_ZN7osw_u1613sw_u16_kernelILi32ELi20ELi512ELb0ELb0EEEvNS_5KArgsE",
-    "pair_db_G32_R28": "_ZN7osw_u1613sw_u16_kernelILi32ELi28ELi512ELb1ELb0EEEvNS_5KArgsE",
-    "pair_db_G4_R36": "_ZN7osw_u1613sw_u16_kernelILi4ELi36ELi384ELb1ELb0EEEvNS_5KArgsE",
+    "two_track_G32_R40": "_ZN7osw_u1613sw_u16_kernelILi32ELi40ELi384ELb0ELb0ELb0EEEvNS_5KArgsE",
+    "two_track_G32_R20": "_ZN7osw_u1613sw_u16_kernelILi32ELi20ELi512ELb0ELb0ELb0EEEvNS_5KArgsE",
+    "pair_db_G32_R28": "_ZN7osw_u1613sw_u16_kernelILi32ELi28ELi512ELb1ELb0ELb0EEEvNS_5KArgsE",
+    "pair_db_G4_R36": "_ZN7osw_u1613sw_u16_kernelILi4ELi36ELi384ELb1ELb0ELb0EEEvNS_5KArgsE",
 }
 
 
