@@ -4,7 +4,7 @@
 TAG=${1:-scale}
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l; nproc
-for N in 1 2 4 8; do
+for N in ${NS:-1 2 4 8}; do
   ARGS="--steps 3 --warmup 2 --no-cpu-baseline"
   [ $N -lt 8 ] && ARGS="$ARGS --no-extra --no-verify"
   if [ $N -eq 1 ]; then CMD="python bench.py --gpus 1 $ARGS"
@@ -15,7 +15,7 @@ done
 python - <<PY
 import json
 v = {}
-for n in (1, 2, 4, 8):
+for n in [int(x) for x in "${NS:-1 2 4 8}".split()]:
     try:
         d = json.load(open("gpurun_out/${TAG}_bench_%dgpu.json" % n))
     except Exception as e:
