@@ -29,11 +29,13 @@ build/%.o: oswald_b200/csrc/host/%.c $(wildcard oswald_b200/csrc/host/*.h) oswal
 oswald_b200/liboswald_cuda.so: $(CUOBJ) build/dbformat.o build/submat.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart_static -lpthread -ldl -lrt -lgomp
 
-# hash of the kernel and layout sources the library was built from: bench.py reports it as `build`
-# and matches it against the tag stored with profiles/ncu_traffic.json
+# hash of the kernel, planner and layout sources the library was built from (not of the host-side
+# orchestration in api.cu or the calibration kernels): bench.py reports it as `build` and matches it
+# against the tag stored with profiles/ncu_traffic.json
+TAGSRC   := $(sort $(wildcard oswald_b200/csrc/cuda/sw_*.cu oswald_b200/csrc/cuda/*.cuh oswald_b200/csrc/cuda/*.h)) \
+            oswald_b200/csrc/cuda/topr.cu oswald_b200/csrc/cuda/plan.cu oswald_b200/csrc/host/dbformat.c oswald_b200/csrc/host/dbformat.h
 oswald_b200/build_tag.txt: oswald_b200/liboswald_cuda.so
-	cat $(sort $(CUSRC)) oswald_b200/csrc/cuda/*.h oswald_b200/csrc/cuda/*.cuh oswald_b200/csrc/host/dbformat.c oswald_b200/csrc/host/dbformat.h \
-	    | sha256sum | cut -c1-12 > $@
+	cat $(TAGSRC) | sha256sum | cut -c1-12 > $@
 
 oswald_b200/oswald: $(CLISRC) oswald_b200/liboswald_cuda.so
 	$(HOSTCC) -O2 -std=gnu11 -Wall -fopenmp -Iinclude -Ioswald_b200/csrc/host -o $@ $(CLISRC) \

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 
 static thread_local char g_err[512];
@@ -226,6 +227,16 @@ extern "C" int osw_init(int n_devices, const int *devices, osw_ctx **out) {
     if (!c->devs) { delete c; return OSW_E_NOMEM; }
     c->n_dev = n_devices;
     c->tune.read();
+    if (n_devices > 1) {
+        // creating a device's primary context takes about a second: do it for all devices at once
+        // (measured with eight GPUs: osw_init 7.9 s one after the other)
+        std::vector<std::thread> warm;
+        for (int i = 0; i < n_devices; ++i) {
+            const int dev = devices ? devices[i] : i;
+            if (dev >= 0 && dev < avail) warm.emplace_back([dev] { if (cudaSetDevice(dev) == cudaSuccess) cudaFree(nullptr); });
+        }
+        for (std::thread &t : warm) t.join();
+    }
     for (int i = 0; i < n_devices; ++i) {
         DevState &d = c->devs[i];
         d.dev = devices ? devices[i] : i;

@@ -2,7 +2,8 @@
 chunk streams with the product's host code (osw_shard_build), scores only its own sequences
 (here with the oracle standing in for the GPU - this is a test of the sharding, gathering and
 host-side top-r merge, not of the kernels), the ranks gather their r hits per query and rank 0
-merges them with osw_merge_hits.  The merged lists must equal the unsharded ranking."""
+merges them with osw_merge_hits.  The merged lists must equal the unsharded ranking.  Every rank also
+takes its shard from the one X.osw file the ranks share: it must be the shard built from the arrays."""
 import ctypes as C
 import os
 import socket
@@ -45,6 +46,19 @@ def _worker(rank, world, port, out_dir):
     L = capi.lib()
     shard = build_shard(L, db, rank, world, 512)
     local = [int(shard.canon[i]) for i in range(shard.n_seqs)]
+    # the same shard from the ONE X.osw file all ranks share (rank 0 writes it)
+    import ctypes as C
+    from test_host import DbFile, shard_fields
+    path = os.path.join(out_dir, "db.osw")
+    if rank == 0:
+        ob.write_db_file(path, db, max_chunk_residues=512)
+    dist.barrier()
+    L.osw_dbfile_open.argtypes = [C.c_char_p, C.POINTER(DbFile)]
+    L.osw_shard_from_file.argtypes = [C.POINTER(DbFile), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(Shard)]
+    f, from_file = DbFile(), Shard()
+    assert L.osw_dbfile_open(path.encode(), C.byref(f)) == 0
+    assert L.osw_shard_from_file(C.byref(f), rank, world, None, None, C.byref(from_file)) == 0
+    assert shard_fields(from_file) == shard_fields(build_shard(L, db, rank, world, f.h.chunk_cols))      # (the file's own work-unit size)
     # this rank's score rows over its own sequences only
     hits = []
     for q in range(queries.n):
