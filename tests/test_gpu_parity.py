@@ -352,6 +352,29 @@ def test_two_gpus_in_one_context(built):
         check(s, db, q, "blosum62", 10, 2, 10)
 
 
+def test_two_gpus_pipelined_and_long_chunk_launches(built, monkeypatch):
+    """The concurrent launch forms (pipelined passes over the longest chunks, the long-chunk launch of
+    small databases) with two GPUs driven by one host thread: every GPU has its own side streams."""
+    import ctypes as C
+    n = C.c_int(0)
+    built.osw_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    monkeypatch.setenv("OSW_PIPE_CHUNKS", "3")
+    monkeypatch.setenv("OSW_LONG_CHUNKS", "5")
+    monkeypatch.setenv("OSW_EXPRESS_RATIO", "0")
+    rng = np.random.default_rng(32)
+    seqs = rand_seqs(rng, 3000, 0, 400) + [AA[rng.integers(0, 20, size=k)] for k in (9000, 30000, 65535, 50000)]
+    db = make_db(seqs)
+    with ob.Searcher(2) as s:
+        s.load_db(db, max_chunk_residues=1024)
+        for lens in ([1500, 2900, 1400], [144], [90, 100], [5478]):
+            q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in lens])
+            want = oracle_scores(q, db, "blosum62", 10, 2)
+            for mode in MODES.values():
+                check(s, db, q, "blosum62", 10, 2, 10, mask=mode, want=want)
+
+
 def test_invalid_inputs_are_rejected(searcher):
     rng = np.random.default_rng(2)
     db = make_db(rand_seqs(rng, 50, 5, 60))
