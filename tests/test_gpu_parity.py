@@ -198,6 +198,25 @@ def test_rescore_in_rounds_when_the_flag_list_is_small(built, monkeypatch):
                 assert tm["rescored_pairs"] == n_over
 
 
+def test_scores_only_and_streamed_file(built, tmp_path):
+    """top = 0 (no hit list, every score on request): the flagged pairs are then found by a scan of their
+    own and re-scored all the same; and a database loaded from X.osw into a context that streams it through
+    device windows."""
+    rng = np.random.default_rng(68)
+    db, q = overflow_case(rng)
+    want = oracle_scores(q, db, "pam30", 9, 1)
+    path = tmp_path / "db.osw"
+    ob.write_db_file(path, db)
+    for window in (0, 1 << 20):
+        with ob.Searcher(1) as s:
+            s.set_device_window(window)
+            s.load_db_file(path)
+            hits, tm, scores = s.search(q, ob.matrix("pam30"), 9, 1, top=0, all_scores=True)
+            assert np.array_equal(scores, want) and all(h == [] for h in hits)
+            assert tm["rescored_pairs"] == int((want + 9 + 1 + 1 + 32 >= 65504).sum()) > 0
+            check(s, db, q, "pam30", 9, 1, 10, want=want)
+
+
 def test_empty_shard_after_an_overflow_search(built):
     """A context whose shard is empty (fewer chunks than shards) must not re-score from the flagged
     count a previous search left behind."""
