@@ -954,9 +954,14 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
     if (c->kernel_mask & OSW_K_U16) {
         std::vector<uint32_t> q_len((size_t)nq);
         for (int q = 0; q < nq; ++q) q_len[q] = q_off[q + 1] - q_off[q];
-        passes.resize(MAX_PASSES);
         const int mode = (c->kernel_mask & OSW_K_PAIR_DB) ? OSW_PLAN_PAIR_DB : (c->kernel_mask & OSW_K_TWO_TRACK) ? OSW_PLAN_TWO_TRACK : OSW_PLAN_AUTO;
-        int n_pass = osw_plan_passes_ex(q_len.data(), nq, passes.data(), MAX_PASSES, mode, 4, c->tune.rmax);
+        // (a pass descriptor is a kilobyte: room for 32 first - nearly every search - and for MAX_PASSES only when needed)
+        passes.resize(32);
+        int n_pass = osw_plan_passes_ex(q_len.data(), nq, passes.data(), 32, mode, 4, c->tune.rmax);
+        if (n_pass < 0) {
+            passes.resize(MAX_PASSES);
+            n_pass = osw_plan_passes_ex(q_len.data(), nq, passes.data(), MAX_PASSES, mode, 4, c->tune.rmax);
+        }
         if (n_pass < 0) { snprintf(g_err, sizeof g_err, "the queries need more than %d passes", MAX_PASSES); return OSW_E_ARG; }
         // A single-pass plan that also fits 32 lanes x <= 16 rows can hand its longest chunks to a
         // launch of that geometry (same halves, same directory; the launcher decides per launch).
