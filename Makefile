@@ -18,7 +18,7 @@ lib: oswald_b200/liboswald_cuda.so oswald_b200/build_tag.txt
 cli: oswald_b200/oswald
 tools: tools/osw_synth tools/libosw_synth.so
 
-build/%.o: oswald_b200/csrc/cuda/%.cu oswald_b200/csrc/cuda/osw_internal.h oswald_b200/csrc/cuda/sw_u16_kernel.cuh include/oswald_cuda.h oswald_b200/csrc/host/dbformat.h
+build/%.o: oswald_b200/csrc/cuda/%.cu oswald_b200/csrc/cuda/osw_internal.h oswald_b200/csrc/cuda/sw_t16.h oswald_b200/csrc/cuda/sw_u16_kernel.cuh include/oswald_cuda.h oswald_b200/csrc/host/dbformat.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 

@@ -58,7 +58,10 @@ enum {
     OSW_K_DEFAULT = 3,
     /* how the two 16-bit halves of the first stage are used (default: chosen per query set) */
     OSW_K_TWO_TRACK = 4,   /* always two query tracks against one database sequence */
-    OSW_K_PAIR_DB = 8      /* always one query track against two database sequences */
+    OSW_K_PAIR_DB = 8,     /* always one query track against two database sequences */
+    OSW_K_TRANSPOSED = 16  /* always the transposed form (database residues as the rows of the array, the query as
+                              the column stream; chosen by itself for short queries when it is faster), whenever the
+                              queries fit it */
 };
 
 typedef struct osw_timing {

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("OSWALD_CUDA_LIB") or os.path.join(_HERE, "liboswald_c
 
 OSW_OK = 0
 OSW_K_U16, OSW_K_I32, OSW_K_DEFAULT = 1, 2, 3
-OSW_K_TWO_TRACK, OSW_K_PAIR_DB = 4, 8
+OSW_K_TWO_TRACK, OSW_K_PAIR_DB, OSW_K_TRANSPOSED = 4, 8, 16
 OSW_SCORE_FLAGGED = 0x7FFFFFFF
 
 

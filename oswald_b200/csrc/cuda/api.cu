@@ -7,6 +7,7 @@
 // and only then waits for all GPUs, orders the r keys per query on the host and merges the
 // GPUs' lists (the reference's sort_scores order, utils.c:3-86).
 #include "osw_internal.h"
+#include "sw_t16.h"
 #include <algorithm>
 #include <chrono>
 #include <new>
@@ -27,8 +28,9 @@ namespace {
 
 constexpr uint32_t MAX_LAUNCH_SLOTS = 4096;
 constexpr uint32_t FLAG_CAPACITY_MIN = 1u << 16;
+constexpr size_t CONTROL_BYTES = MAX_LAUNCH_SLOTS * sizeof(unsigned long long) + 2 * sizeof(unsigned long long) + (1 + MAX_LAUNCH_SLOTS) * sizeof(uint32_t);
 
-struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; uint32_t express; uint32_t slot; uint32_t x_chunks, x_ctas; int x_R; uint32_t pipe_chunks; };
+struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; uint32_t express; uint32_t slot; uint32_t x_chunks, x_ctas; int x_R; uint32_t pipe_chunks; int transposed; };
 
 struct DevState {
     int dev = -1, n_sms = 0;
@@ -69,11 +71,13 @@ struct DevState {
     uint32_t *d_counters = nullptr;            // [0] flagged count, [1..] chunk counters per launch
     unsigned long long *d_task_counter = nullptr;   // [0] i32 queue, [1] n_tasks mirror
     unsigned long long *d_cycles = nullptr;    // [MAX_LAUNCH_SLOTS]
+    unsigned char *d_control = nullptr;        // the three above live in this one buffer (cleared by one memset per search)
     TopRWork topr = {}; int topr_nq = 0; uint32_t topr_r = 0;
     unsigned long long *h_keys = nullptr; size_t h_keys_cap = 0;      // pinned
     int32_t *h_scores = nullptr; size_t h_scores_cap = 0;             // pinned
     unsigned long long *h_cycles = nullptr;                            // pinned [MAX_LAUNCH_SLOTS]
     uint32_t *h_counts = nullptr;                                       // pinned [4]
+    std::vector<uint32_t> t16_hist;            // the shard's pairs by length (sw_t16.h), made at the first search that looks at it
 };
 
 template <typename T>
@@ -107,6 +111,7 @@ void free_db(DevState &d) {
     cudaFree(d.d_bound); d.bound_cap = 0;
     d.d_stream = nullptr; d.d_chunks = nullptr; d.d_pair_chunks = nullptr; d.d_canon = nullptr; d.d_seq_off = nullptr; d.d_seq_len = nullptr;
     d.d_bound = nullptr;
+    d.t16_hist.clear();
     if (d.h_stream) cudaFreeHost(d.h_stream);
     d.h_stream = nullptr;
     osw_shard_free(&d.shard);
@@ -146,6 +151,7 @@ struct Tunables {
     int      rmax = 0;                  // OSW_RMAX: rows per lane of the full-height passes (0 = default)
     int      long_chunks = -1;          // OSW_LONG_CHUNKS: force the number of chunks of the long-chunk launch (0 = never)
     int      pipe_chunks = -1;          // OSW_PIPE_CHUNKS: force the number of chunks whose passes are pipelined (0 = never)
+    int      transpose = -1;            // OSW_TRANSPOSE: 0 = never the transposed form (sw_t16.cu), 1 = whenever the queries fit it
     bool     trace = false;             // OSW_TRACE: per-launch report on stderr
     void read() {
         if (const char *e = getenv("OSW_CHUNK_COLS")) { const int v = atoi(e); if (v >= 64) chunk_cols = (uint32_t)v; }
@@ -158,6 +164,7 @@ struct Tunables {
         if (const char *e = getenv("OSW_RMAX")) rmax = atoi(e);
         if (const char *e = getenv("OSW_LONG_CHUNKS")) long_chunks = atoi(e);
         if (const char *e = getenv("OSW_PIPE_CHUNKS")) pipe_chunks = atoi(e);
+        if (const char *e = getenv("OSW_TRANSPOSE")) transpose = atoi(e);
         trace = getenv("OSW_TRACE") != nullptr;
     }
 };
@@ -267,13 +274,14 @@ extern "C" int osw_init(int n_devices, const int *devices, osw_ctx **out) {
             (e = cudaMalloc(&d.d_first_table, 1024 * 16 * sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_profile_x, OSW_PROFILE_BYTES)) != cudaSuccess ||
             (e = cudaMalloc(&d.d_first_table_x, 1024 * 16 * sizeof(uint32_t))) != cudaSuccess ||
-            (e = cudaMalloc(&d.d_counters, (1 + MAX_LAUNCH_SLOTS) * sizeof(uint32_t))) != cudaSuccess ||
-            (e = cudaMalloc(&d.d_task_counter, 2 * sizeof(unsigned long long))) != cudaSuccess ||
-            (e = cudaMalloc(&d.d_cycles, MAX_LAUNCH_SLOTS * sizeof(unsigned long long))) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_control, CONTROL_BYTES)) != cudaSuccess ||
             (e = cudaMallocHost(&d.h_cycles, MAX_LAUNCH_SLOTS * sizeof(unsigned long long))) != cudaSuccess ||
             (e = cudaMallocHost(&d.h_counts, 4 * sizeof(uint32_t))) != cudaSuccess) {
             osw_free(c); return cuda_fail(e, "cudaMalloc", __LINE__);
         }
+        d.d_cycles = reinterpret_cast<unsigned long long *>(d.d_control);
+        d.d_task_counter = d.d_cycles + MAX_LAUNCH_SLOTS;
+        d.d_counters = reinterpret_cast<uint32_t *>(d.d_task_counter + 2);
     }
     *out = c;
     return OSW_OK;
@@ -289,7 +297,7 @@ extern "C" void osw_free(osw_ctx *c) {
         free_db(d);
         cudaFree(d.d_scores); cudaFree(d.d_queries); cudaFree(d.d_qoff); cudaFree(d.d_matrix); cudaFree(d.d_scratch);
         cudaFree(d.d_profile); cudaFree(d.d_first_table); cudaFree(d.d_profile_x); cudaFree(d.d_first_table_x);
-        cudaFree(d.d_pairs); cudaFree(d.d_counters); cudaFree(d.d_task_counter); cudaFree(d.d_cycles);
+        cudaFree(d.d_pairs); cudaFree(d.d_control);
         cudaFree(d.topr.hist); cudaFree(d.topr.prefix); cudaFree(d.topr.remaining); cudaFree(d.topr.out_count); cudaFree(d.topr.out_keys);
         if (d.h_keys) cudaFreeHost(d.h_keys);
         if (d.h_scores) cudaFreeHost(d.h_scores);
@@ -548,7 +556,7 @@ struct LaunchModel {
 
 int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32_t *q_off, int nq,
                    const int8_t *matrix, int go, int ge, uint32_t top_r, bool want_all,
-                   const std::vector<OswPass> &passes, const OswPass *pass_x,
+                   const std::vector<OswPass> &passes, const OswPass *pass_x, const OswT16Plan *tplan,
                    uint32_t *n_launch_slots, uint64_t *launches, uint64_t *padded_cells) {
     const osw_shard &s = d.shard;
     const uint64_t N = s.n_seqs;
@@ -605,9 +613,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
     CK(cudaMemcpyAsync(d.d_matrix, matrix, 24 * 32, cudaMemcpyHostToDevice, d.st));
     CK(cudaEventRecord(d.ev[0], d.st));
     CK(cudaMemsetAsync(d.d_scores, 0, (size_t)nq * N * sizeof(int32_t), d.st));
-    CK(cudaMemsetAsync(d.d_counters, 0, (1 + MAX_LAUNCH_SLOTS) * sizeof(uint32_t), d.st));
-    CK(cudaMemsetAsync(d.d_task_counter, 0, 2 * sizeof(unsigned long long), d.st));
-    CK(cudaMemsetAsync(d.d_cycles, 0, MAX_LAUNCH_SLOTS * sizeof(unsigned long long), d.st));
+    CK(cudaMemsetAsync(d.d_control, 0, CONTROL_BYTES, d.st));          // counters, task queue, cycle sums: one clear
 
     uint32_t slot = 0;
     d.trace.clear();
@@ -620,7 +626,24 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             CK(cudaMemcpyAsync(d.d_pair, d.h_pair, 2 * s.pair_cols, cudaMemcpyHostToDevice, d.st));
         }
     }
-    if (use_u16 && N) {
+    if (use_u16 && N && tplan && tplan->warps) {
+        // The transposed form (sw_t16.cu): one launch scores every pair of sequences against every query.
+        if (slot + OSW_T16_CLASSES > MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
+        OswT16Params tp;
+        tp.stream = d.d_stream; tp.seq_off = d.d_seq_off; tp.seq_len = d.d_seq_len;
+        tp.queries = d.d_queries; tp.q_off = d.d_qoff; tp.nq = nq; tp.matrix = d.d_matrix;
+        tp.scores = d.d_scores; tp.n_seqs = N;
+        tp.counters = d.d_counters + 1 + slot; tp.cycle_acc = d.d_cycles + slot;
+        tp.gap_open_extend = go + ge; tp.gap_extend = ge;
+        if (osw_launch_t16(tp, *tplan, d.n_sms, d.st) != OSW_OK) { cuda_fail(cudaGetLastError(), "sw_t16 launch", __LINE__); return OSW_E_CUDA; }
+        LaunchRecord lr = {};
+        lr.end = tplan->n_pairs; lr.cols = (uint64_t)nq * s.n_residues; lr.slot = slot; lr.transposed = tplan->warps;
+        lr.first = tplan->class_begin[1]; lr.x_chunks = tplan->class_begin[2]; lr.x_ctas = tplan->class_begin[3];
+        d.trace.push_back(lr);
+        slot += OSW_T16_CLASSES; *launches += 1;
+        *padded_cells += tplan->padded_cells;
+        CK(cudaEventRecord(d.ev[1], d.st));
+    } else if (use_u16 && N) {
         uint64_t bound_col0 = 0, win_col0 = 0;
         const uint8_t *win_ptr = nullptr;             // streaming mode: the device window holding the current segment
         // pair-database passes walk the pair directory and the pair stream, the others the plain ones
@@ -998,13 +1021,55 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
         passes.resize((size_t)n_pass);
     }
     const bool use_u16 = (c->kernel_mask & OSW_K_U16) != 0;
+    // The transposed form (sw_t16.cu: database residues as rows, the query as the column stream) takes
+    // short queries whenever its model says it is faster than the passes planned above - small
+    // databases, whose launches last as long as the walk along their longest sequence, above all.
+    std::vector<OswT16Plan> tplans;
+    double t16_est = 0;
+    if (use_u16 && c->tune.transpose != 0 && !(c->kernel_mask & (OSW_K_TWO_TRACK | OSW_K_PAIR_DB))) {
+        bool ok = true;
+        for (int i = 0; i < c->n_dev; ++i) ok &= !c->devs[i].streaming && (c->devs[i].shard.n_seqs == 0 || c->devs[i].d_stream != nullptr);
+        if (ok) {
+            tplans.resize((size_t)c->n_dev);
+            for (int i = 0; i < c->n_dev && ok; ++i) {
+                DevState &d = c->devs[i];
+                if (d.t16_hist.empty()) {
+                    d.t16_hist.resize(OSW_T16_MAX_ROWS32 + 1);
+                    osw_t16_histogram(d.shard.seq_len, d.shard.n_seqs, d.t16_hist.data());
+                }
+                osw_t16_plan(d.t16_hist.data(), d.shard.n_seqs, q_off, nq, d.n_sms, &tplans[(size_t)i]);
+                ok &= d.shard.n_seqs == 0 || tplans[(size_t)i].warps != 0;
+            }
+        }
+        const bool forced = (c->kernel_mask & OSW_K_TRANSPOSED) || c->tune.transpose == 1;
+        if (ok && !forced) {
+            // the passes' own estimate, on the first GPU's shard (all shards hold the same mix of lengths)
+            const DevState &d0 = c->devs[0];
+            const osw_shard &s0 = d0.shard;
+            const bool pd = !passes.empty() && passes[0].pair_db != 0;
+            const double cols = (double)(pd ? s0.pair_cols : s0.n_residues);
+            const double longest = !(pd ? s0.n_pair_chunks : s0.n_chunks) ? 0.0 : (double)(pd ? s0.pair_chunks[0].n_pair_cols : s0.chunks[0].n_cols);
+            double t_std = 0;
+            for (const OswPass &ps : passes) {
+                const LaunchModel m(ps.G, ps.R, pd, cols, d0.n_sms);
+                const double t_chain = longest * m.alone;
+                t_std += std::max(m.t_pipe, t_chain) + 0.25 * std::min(m.t_pipe, t_chain) + 6000.0;      // (+ a launch and its profile build)
+            }
+            // (both models are optimistic, the passes' one more so on databases of this size: measured / model is
+            // 1.1-1.25 here and 1.25-1.65 there - profiles/r2_transposed_form.md)
+            ok = s0.n_seqs != 0 && tplans[0].est_cycles < 1.25 * t_std;
+        }
+        if (!ok) tplans.clear();
+        else t16_est = tplans[0].est_cycles;
+    }
     uint64_t launches = 0, padded = 0, rescored = 0;
     std::vector<uint32_t> slots((size_t)c->n_dev, 0u);
 
     // ---- phase 1: first stage on every GPU ------------------------------------------------
     for (int i = 0; i < c->n_dev; ++i) {
         int rc = enqueue_search(c, c->devs[i], queries, q_off, nq, matrix, go, ge, (uint32_t)top_r,
-                                all_scores != nullptr, passes, have_x ? &plan_x : nullptr, &slots[i], &launches, &padded);
+                                all_scores != nullptr, passes, have_x ? &plan_x : nullptr, tplans.empty() ? nullptr : &tplans[(size_t)i],
+                                &slots[i], &launches, &padded);
         if (rc != OSW_OK) return rc;
     }
     const double t_h2d = now_ms();
@@ -1115,6 +1180,11 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
             for (uint32_t k = 0; k < d.trace.size(); ++k) {
                 const LaunchRecord &lr = d.trace[k];
                 const unsigned long long cyc = std::max<unsigned long long>(d.h_cycles[lr.slot], 1);
+                if (lr.transposed) {
+                    fprintf(stderr, "osw trace: launch %u/%zu transposed, %d warps per CTA, %u pairs (gang classes up to rank %u / %u / %u)  %llu busy cycles/SM  %.2f padded cells/SM-clk  model %.0f cycles\n",
+                            k + 1, d.trace.size(), lr.transposed, lr.end, lr.first, lr.x_chunks, lr.x_ctas, cyc / d.n_sms, (double)padded / (double)cyc, t16_est);
+                    continue;
+                }
                 const double cells = 2.0 * lr.G * lr.R * (double)lr.cols;
                 fprintf(stderr, "osw trace: launch %u/%zu G=%d R=%d in=%d out=%d pairdb=%d express=%u long[R=%d chunks=%u ctas=%u] pipelined=%u chunks [%u,%u)  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
                         k + 1, d.trace.size(), lr.G, lr.R, lr.has_in, lr.has_out, lr.pair_db, lr.express, lr.x_R, lr.x_chunks, lr.x_ctas, lr.pipe_chunks, lr.first, lr.end,

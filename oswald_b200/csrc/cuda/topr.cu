@@ -103,31 +103,55 @@ topr_gather_kernel(const int32_t *scores, const uint32_t *canon, uint64_t n, uin
 // Small databases (n <= TOPR_SMALL_MAX): the whole selection in ONE launch, one CTA per query.  The
 // keys are read from global memory once, into shared memory; the radix rounds and the final gather
 // work there (a tiny search is bound by launch count, not by the scan: 7 launches -> 1).
-constexpr int SMALL_THREADS = 512;
+constexpr int SMALL_THREADS = 1024, SMALL_WARPS = SMALL_THREADS / 32;
+
 __global__ void __launch_bounds__(SMALL_THREADS)
 topr_small_kernel(const int32_t *scores, const uint32_t *canon, uint32_t n, uint32_t r, Rounds rd, TopRWork w, FlagList fl) {
     extern __shared__ __align__(16) unsigned long long s_keys[];     // [n]
-    __shared__ uint32_t hist[256], suffix[256];
-    __shared__ unsigned long long s_pre;
+    // (a histogram per warp: the scores of a search cluster in a few dozen values, and thousands of atomics on
+    // one shared-memory word serialise)
+    __shared__ uint32_t hist_w[SMALL_WARPS][256], hist[256], suffix[256];
+    __shared__ unsigned long long s_pre, s_or, s_and;
     __shared__ uint32_t s_need, s_count;
-    const int q = blockIdx.x;
+    const int q = blockIdx.x, wid = threadIdx.x >> 5;
     const int32_t *row = scores + (size_t)q * n;
+    if (threadIdx.x == 0) { s_pre = 0; s_need = r; s_count = 0; s_or = 0; s_and = ~0ull; }
+    __syncthreads();
+    unsigned long long k_or = 0, k_and = ~0ull;
     for (uint32_t i = threadIdx.x; i < n; i += SMALL_THREADS) {
         const int sc = row[i];
         if (sc == OSW_SCORE_FLAGGED && fl.count) list_flagged(fl, (uint32_t)q, i);
-        s_keys[i] = make_key(sc, canon[i]);
+        const unsigned long long k = make_key(sc, canon[i]);
+        s_keys[i] = k;
+        k_or |= k; k_and &= k;
     }
-    if (threadIdx.x == 0) { s_pre = 0; s_need = r; s_count = 0; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { k_or |= __shfl_xor_sync(0xffffffffu, k_or, o); k_and &= __shfl_xor_sync(0xffffffffu, k_and, o); }
+    if ((threadIdx.x & 31) == 0) { atomicOr(&s_or, k_or); atomicAnd(&s_and, k_and); }
     __syncthreads();
+    const unsigned long long differ = s_or ^ s_and;           // bits in which the keys are not all alike
     for (int j = 0; j < rd.n; ++j) {
-        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
-        __syncthreads();
         const int shift = rd.shift[j];
         const unsigned long long himask = j ? ~0ull << (rd.shift[j - 1]) : 0ull, pre = s_pre;
         const uint32_t need = s_need;
+        if (((differ >> shift) & 255ull) == 0) {              // every key has the same digit here: no counting needed
+            __syncthreads();
+            if (threadIdx.x == 0) s_pre = pre | (s_or & (255ull << shift));
+            __syncthreads();
+            continue;
+        }
+        for (int v = threadIdx.x; v < SMALL_WARPS * 256; v += SMALL_THREADS) (&hist_w[0][0])[v] = 0;
+        __syncthreads();
         for (uint32_t i = threadIdx.x; i < n; i += SMALL_THREADS) {
             const unsigned long long k = s_keys[i];
-            if ((k & himask) == pre) atomicAdd(&hist[(k >> shift) & 255], 1u);
+            if ((k & himask) == pre) atomicAdd(&hist_w[wid][(k >> shift) & 255], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int v = 0; v < SMALL_WARPS; ++v) sum += hist_w[v][threadIdx.x];
+            hist[threadIdx.x] = sum;
         }
         __syncthreads();
         if (threadIdx.x < 32) {          // one warp: suffix sums over the 256 bins (8 per lane), then the pick

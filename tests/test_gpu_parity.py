@@ -74,10 +74,13 @@ def test_golden_cases(searcher, name, mask):
 
 
 MODES = {"auto": capi.OSW_K_DEFAULT, "two_track": capi.OSW_K_DEFAULT | capi.OSW_K_TWO_TRACK,
-         "pair_db": capi.OSW_K_DEFAULT | capi.OSW_K_PAIR_DB}
+         "pair_db": capi.OSW_K_DEFAULT | capi.OSW_K_PAIR_DB,
+         # database residues as rows, the query as the column stream (sw_t16.cu); falls back to the passes
+         # above for queries that do not fit it, and is what "auto" picks for short queries on small databases
+         "transposed": capi.OSW_K_DEFAULT | capi.OSW_K_TRANSPOSED}
 
 
-@pytest.mark.parametrize("mode", ["auto", "two_track", "pair_db"])
+@pytest.mark.parametrize("mode", ["auto", "two_track", "pair_db", "transposed"])
 @pytest.mark.parametrize("lengths", [[144], [5, 37, 144, 189], [1, 1, 2], [144, 189, 222, 375, 464, 567, 657],
                                       [1000, 1500], [2005], [1537, 3005]])
 def test_random_db_all_query_geometries(searcher, lengths, mode):
@@ -444,7 +447,7 @@ def test_fuzz_small_cases(searcher):
         go, ge = int(rng.integers(0, 30)), int(rng.integers(0, 6))
         top = int(rng.choice([1, 3, 10, 50, n + 5]))
         searcher.load_db(db, max_chunk_residues=int(rng.choice([0, 0, 32, 200, 1000])))
-        mode = list(MODES.values())[case % 3]
+        mode = list(MODES.values())[case % len(MODES)]
         check(searcher, db, q, name, go, ge, top, mask=mode)
 
 
@@ -604,3 +607,33 @@ def test_many_tiny_queries(built):
         s.load_db(db)
         tm = check(s, db, q, "blosum62", 10, 2, 3)
         assert tm["score_launches"] >= 2
+
+
+@pytest.mark.parametrize("transpose", ["1", "-1"])
+def test_transposed_form(built, monkeypatch, transpose):
+    """The transposed first stage (sw_t16.cu): one warp per pair of sequences, gangs of 2, 4 and 8 warps for
+    the long ones (bottom rows handed from block to block through tagged ring entries), 8- and 4-warp CTAs
+    (queries up to 248 / 1024 residues), several queries, empty sequences and queries, an odd number of
+    sequences, W-rich sequences - forced (OSW_TRANSPOSE=1) and as the model picks it (-1)."""
+    monkeypatch.setenv("OSW_TRANSPOSE", transpose)
+    rng = np.random.default_rng(404)
+    W = np.uint8(19)
+    seqs = ([np.zeros(0, np.uint8)] * 3 + rand_seqs(rng, 1200, 1, 700) +
+            [AA[rng.integers(0, 20, size=n)] for n in (255, 256, 257, 511, 513, 1023, 1025, 2047, 2049, 2500, 4097, 9000, 16385, 36000, 65535)] +
+            [np.full(7000, W, dtype=np.uint8)])
+    db = make_db(seqs)
+    with ob.Searcher(1) as s:
+        s.load_db(db)
+        for lens in ([144], [1], [31], [32], [33], [248], [249], [90, 100], [33, 150, 7, 61, 0, 200], [400], [1000], [1024, 3], [97] * 9, [500] * 8):
+            q = ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in lens])
+            tm = check(s, db, q, "blosum62", 10, 2, 10)
+        # (with queries of at most 1024 residues and substitution scores of at most 31 no score of this form reaches
+        # the 16-bit flag threshold; the largest it sees here is 1000 x 13)
+        q = ob.Queries.from_list([np.full(1000, W, dtype=np.uint8), AA[rng.integers(0, 20, size=77)]])
+        check(s, db, q, "pam30", 9, 1, 5)
+    # tiny databases: fewer pairs than warps, a single sequence
+    with ob.Searcher(1) as s:
+        for n in (1, 2, 3, 40):
+            db = make_db(rand_seqs(rng, n, 1, 3000))
+            s.load_db(db)
+            check(s, db, ob.Queries.from_list([AA[rng.integers(0, 20, size=m)] for m in (144, 20)]), "blosum50", 10, 2, 4)

@@ -15,7 +15,7 @@ with ob.Searcher(1) as s:
     s.load_db(db, max_chunk_residues=512)
     for ql in ([60], [144, 189], [700, 1500], [1400, 1350, 90]):
         q = ob.Queries.from_list([aa[rng.integers(0, 20, size=m)] for m in ql])
-        for mask in (capi.OSW_K_DEFAULT, capi.OSW_K_DEFAULT | capi.OSW_K_TWO_TRACK, capi.OSW_K_DEFAULT | capi.OSW_K_PAIR_DB, capi.OSW_K_I32):
+        for mask in (capi.OSW_K_DEFAULT, capi.OSW_K_DEFAULT | capi.OSW_K_TWO_TRACK, capi.OSW_K_DEFAULT | capi.OSW_K_PAIR_DB, capi.OSW_K_DEFAULT | capi.OSW_K_TRANSPOSED, capi.OSW_K_I32):
             s.set_kernels(mask)
             hits, tm = s.search(q, ob.matrix("blosum62"), 10, 2, top=5)
 print("sanitize case done")
