@@ -152,6 +152,7 @@ struct Tunables {
     int      long_chunks = -1;          // OSW_LONG_CHUNKS: force the number of chunks of the long-chunk launch (0 = never)
     int      pipe_chunks = -1;          // OSW_PIPE_CHUNKS: force the number of chunks whose passes are pipelined (0 = never)
     int      transpose = -1;            // OSW_TRANSPOSE: 0 = never the transposed form (sw_t16.cu), 1 = whenever the queries fit it
+    double   t16_gang = 1.2;            // OSW_T16_GANG: its gang threshold, as a fraction of the launch's estimated time
     bool     trace = false;             // OSW_TRACE: per-launch report on stderr
     void read() {
         if (const char *e = getenv("OSW_CHUNK_COLS")) { const int v = atoi(e); if (v >= 64) chunk_cols = (uint32_t)v; }
@@ -165,6 +166,7 @@ struct Tunables {
         if (const char *e = getenv("OSW_LONG_CHUNKS")) long_chunks = atoi(e);
         if (const char *e = getenv("OSW_PIPE_CHUNKS")) pipe_chunks = atoi(e);
         if (const char *e = getenv("OSW_TRANSPOSE")) transpose = atoi(e);
+        if (const char *e = getenv("OSW_T16_GANG")) t16_gang = atof(e);
         trace = getenv("OSW_TRACE") != nullptr;
     }
 };
@@ -1037,7 +1039,7 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
                     d.t16_hist.resize(OSW_T16_MAX_ROWS32 + 1);
                     osw_t16_histogram(d.shard.seq_len, d.shard.n_seqs, d.t16_hist.data());
                 }
-                osw_t16_plan(d.t16_hist.data(), d.shard.n_seqs, q_off, nq, d.n_sms, &tplans[(size_t)i]);
+                osw_t16_plan(d.t16_hist.data(), d.shard.n_seqs, q_off, nq, d.n_sms, c->tune.t16_gang, &tplans[(size_t)i]);
                 ok &= d.shard.n_seqs == 0 || tplans[(size_t)i].warps != 0;
             }
         }
@@ -1055,9 +1057,10 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
                 const double t_chain = longest * m.alone;
                 t_std += std::max(m.t_pipe, t_chain) + 0.25 * std::min(m.t_pipe, t_chain) + 6000.0;      // (+ a launch and its profile build)
             }
-            // (both models are optimistic, the passes' one more so on databases of this size: measured / model is
-            // 1.1-1.25 here and 1.25-1.65 there - profiles/r2_transposed_form.md)
-            ok = s0.n_seqs != 0 && tplans[0].est_cycles < 1.25 * t_std;
+            // (the passes' model is optimistic on databases of this size: measured / model is 1.25-1.65, against
+            // 0.95-1.1 for the transposed form's; 8-warp CTAs - queries of more than about 250 residues - have two
+            // warps per scheduler and are slower than the passes everywhere: profiles/r2_transposed_form.md)
+            ok = s0.n_seqs != 0 && tplans[0].warps == 16 && tplans[0].est_cycles < 1.4 * t_std;
         }
         if (!ok) tplans.clear();
         else t16_est = tplans[0].est_cycles;

@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 
 namespace osw_t16 {
 
@@ -91,17 +92,18 @@ __device__ __forceinline__ uint32_t sweep(const unsigned char *tbl, const uint16
     const uint32_t gin = IO == 2 ? (uint32_t)__cvta_generic_to_shared(ring_in) : 0u, gout = IO == 2 ? (uint32_t)__cvta_generic_to_shared(ring_out) : 0u;
     uint4 ent = make_uint4(B2, B2, tag_task, blk);
     if (IO == 2 && has_in) ent = lds_volatile(gin);
-#pragma unroll 2
-    for (int s = 0; s < n_steps; ++s) {
+    // One step; LOAD: lane 0's top-row entry of the next column is read (IO = 1: columns below m - 1 only - past
+    // the query's end lane 0 keeps the last column's entry, whose H the block above has counted already; anything
+    // else could raise the maximum), OUT: lane 31 is at a column >= 0 and leaves its bottom row.
+    auto step = [&](const int s, auto load_c, auto out_c) {
+        constexpr bool LOAD = decltype(load_c)::value, OUT = decltype(out_c)::value;
         // the next steps' reads first: the column entry two steps ahead, the table words one step ahead
         const uint32_t qo2 = qcol[s + 2];
         const uint4 n0 = *reinterpret_cast<const uint4 *>(tbl + qo1);
         uint4 n1 = n0;
         if (R > 4) n1 = *reinterpret_cast<const uint4 *>(tbl + qo1 + QUAD_BYTES);
-        // (lane 0 is past the query's end from step m on; there it keeps reading the last column's entry, whose H
-        // the block above has counted already - anything else could raise the maximum)
         uint2 top_next = top;
-        if (IO == 1 && has_in) top_next = rin[min(s + 1, m - 1)];
+        if (IO == 1 && LOAD && has_in) top_next = rin[s + 1];
         uint4 ent_next = ent;
         if (IO == 2 && has_in) ent_next = lds_volatile(gin + 16u * (uint32_t)min(s + 1, m - 1));
         // the row above: the lane above's outputs of the previous step, i.e. for this column
@@ -130,9 +132,31 @@ __device__ __forceinline__ uint32_t sweep(const unsigned char *tbl, const uint16
         if (R & 1) C = __vmaxu2(C, Hprev);
         diag = Hup;                                      // H of the row above in this column = the next column's diagonal
         Hbot = Hl[R - 1]; Fbot = F;
-        if (IO == 1 && out_lane && s >= 31) rout[s - 31] = make_uint2(Hbot, Fbot);
+        if (IO == 1 && OUT && out_lane) rout[s - 31] = make_uint2(Hbot, Fbot);
         if (IO == 2 && out_lane && s >= 31) sts_volatile(gout + 16u * (uint32_t)(s - 31), Hbot, Fbot, tag_task, blk + 1);
         v0 = n0; v1 = n1; qo1 = qo2; top = top_next; ent = ent_next;
+    };
+    const std::true_type yes;
+    const std::false_type no;
+    if (IO == 1) {
+        // three stretches of steps, so that no step has to test where it is: lane 31 before its first column,
+        // (both ends inside the query), lane 0 past its last column
+        const int b1 = min(31, m - 1), b2 = max(31, m - 1);
+        int s = 0;
+#pragma unroll 2
+        for (; s < b1; ++s) step(s, yes, no);
+        if (m > 32) {
+#pragma unroll 2
+            for (; s < b2; ++s) step(s, yes, yes);
+        } else {
+#pragma unroll 2
+            for (; s < b2; ++s) step(s, no, no);
+        }
+#pragma unroll 2
+        for (; s < n_steps; ++s) step(s, no, yes);
+    } else {
+#pragma unroll 2
+        for (int s = 0; s < n_steps; ++s) step(s, yes, yes);
     }
     return C;
 }
@@ -314,9 +338,11 @@ sw_t16_kernel(const TArgs a) {
 }
 
 // ---- host side: cost model, classes, launch ----
-// ALU-pipe cycles one warp needs for a step of R rows (4.5 DPX instructions per row and a few more for the
-// step, at one per two cycles), and the time a step takes from start to end (two shuffles, then the row chain).
-inline double step_issue(int R) { return 2.0 * (4.5 * R + 5.0); }
+// Scheduler cycles one warp needs for a step of R rows (4.5 DPX instructions per row and about five more for the
+// step, at one per two cycles, on a pipe that is 72 % busy with four warps per scheduler: measured, 64 cycles at
+// R = 4 - profiles/r2_transposed_form.md), and the time a step takes from start to end (two shuffles, then the row
+// chain; the scheduler's other warps take their turns).
+inline double step_issue(int R) { return 2.8 * (4.5 * R + 5.0); }
 inline double step_time(int R, int warps_per_scheduler) { return std::max(45.0 + 15.0 * R, warps_per_scheduler * step_issue(R)); }
 inline void block_geometry(uint32_t rows32, int g, int rmax, uint32_t *n_blocks, int *R) {
     const uint32_t per_round = (uint32_t)(rmax * g);
@@ -334,7 +360,7 @@ void osw_t16_histogram(const uint32_t *seq_len, uint64_t n_seqs, uint32_t *hist)
     }
 }
 
-void osw_t16_plan(const uint32_t *hist, uint64_t n_seqs, const uint32_t *q_off, int nq, int n_sms, OswT16Plan *plan) {
+void osw_t16_plan(const uint32_t *hist, uint64_t n_seqs, const uint32_t *q_off, int nq, int n_sms, double gang_fraction, OswT16Plan *plan) {
     using namespace osw_t16;
     memset(plan, 0, sizeof *plan);
     if (nq < 1 || n_seqs == 0) return;
@@ -342,6 +368,7 @@ void osw_t16_plan(const uint32_t *hist, uint64_t n_seqs, const uint32_t *q_off, 
     uint64_t m_sum = 0;
     for (int q = 0; q < nq; ++q) { m_max = std::max(m_max, q_off[q + 1] - q_off[q]); m_sum += q_off[q + 1] - q_off[q]; }
     if (m_sum == 0 || m_sum > 4096 || m_max > 1024) return;
+    if ((n_seqs + 1) / 2 * (uint64_t)nq >= (1ull << 28)) return;          // (task numbers are 28-bit tags of the ring entries)
     const uint32_t q_cols = (uint32_t)m_sum + Q_STRIDE_PAD * (uint32_t)nq;
     const uint32_t m_pad = (m_max + 3) & ~3u;
     // 16 warps with 4 rows per lane when the rings of the query's length fit beside their tables, else 8 warps
@@ -370,14 +397,16 @@ void osw_t16_plan(const uint32_t *hist, uint64_t n_seqs, const uint32_t *q_off, 
             padded += (uint64_t)hist[r32] * nb * 32u * (uint32_t)R * 2u * (uint64_t)steps;
         }
     }
-    const double t_thr = work / ((double)std::max(n_sms, 1) * 4.0) / (wps >= 4 ? 0.72 : 0.52) + 4000.0;      // (two warps per scheduler do not hide the row chain)
+    const double t_thr = work / ((double)std::max(n_sms, 1) * 4.0) * (wps >= 4 ? 1.0 : 1.4) + 4000.0;      // (two warps per scheduler do not hide the row chain)
     // gangs: the smallest one that finishes a task in a fraction of the launch's time; classes are ranges
     // of the descending length order, so the gang size may only shrink along it
     const double steps_max = (double)m_max + 31.0;
     auto task_time = [&](uint32_t r32, int g) {
         uint32_t nb; int R;
         block_geometry(r32, g, rmax, &nb, &R);
-        return ((double)(nb / g) * steps_max + (g - 1) * 40.0) * step_time(R, wps) + (double)(nb / g) * 1500.0;
+        if (g == 1) return (double)nb * (steps_max * step_time(R, wps) + 1500.0);
+        // (a gang's warps start 36 steps apart, and its steps poll the ring entries)
+        return ((double)(nb / g) * steps_max + (g - 1) * 36.0 + 31.0) * step_time(R, wps) * 1.15 + (double)(nb / g) * 1500.0;
     };
     uint32_t count[OSW_T16_CLASSES] = {0, 0, 0, 0};          // pairs per class
     int cls_cur = 0;
@@ -385,7 +414,7 @@ void osw_t16_plan(const uint32_t *hist, uint64_t n_seqs, const uint32_t *q_off, 
     for (uint32_t r32 = OSW_T16_MAX_ROWS32; r32 >= 1; --r32) {
         if (!hist[r32]) continue;
         int cls = OSW_T16_CLASSES - 1;                        // the smallest gang that is fast enough, not larger than the class before
-        while (cls > cls_cur && task_time(r32, gang_size(W, cls)) > 0.7 * t_thr) --cls;
+        while (cls > cls_cur && task_time(r32, gang_size(W, cls)) > gang_fraction * t_thr) --cls;
         cls_cur = cls;
         if (t_longest == 0) t_longest = task_time(r32, gang_size(W, cls));
         count[cls] += hist[r32];
@@ -418,4 +447,25 @@ int osw_launch_t16(const OswT16Params &p, const OswT16Plan &plan, int n_ctas, cu
         sw_t16_kernel<8><<<n_ctas, 32 * plan.warps, plan.smem_bytes, st>>>(a);
     }
     return cudaGetLastError() == cudaSuccess ? OSW_OK : OSW_E_CUDA;
+}
+
+// ---- test hooks (CPU tests; not in include/oswald_cuda.h) ----
+extern "C" int osw_t16_plan_probe(const uint32_t *seq_len, uint64_t n_seqs, const uint32_t *q_off, int nq, int n_sms, double gang_fraction,
+                                  uint32_t *class_begin, int *gang_sizes, int *warps, int *rmax, double *est_cycles, uint64_t *padded_cells) {
+    if (!seq_len || !q_off || !class_begin || !gang_sizes || !warps || !rmax) return OSW_E_ARG;
+    uint32_t *hist = new uint32_t[OSW_T16_MAX_ROWS32 + 1];
+    osw_t16_histogram(seq_len, n_seqs, hist);
+    OswT16Plan plan;
+    osw_t16_plan(hist, n_seqs, q_off, nq, n_sms, gang_fraction, &plan);
+    delete[] hist;
+    for (int i = 0; i <= OSW_T16_CLASSES; ++i) class_begin[i] = plan.class_begin[i];
+    for (int i = 0; i < OSW_T16_CLASSES; ++i) gang_sizes[i] = plan.warps ? osw_t16::gang_size(plan.warps, i) : 0;
+    *warps = plan.warps; *rmax = plan.rmax;
+    if (est_cycles) *est_cycles = plan.est_cycles;
+    if (padded_cells) *padded_cells = plan.padded_cells;
+    return OSW_OK;
+}
+// Blocks and rows per lane of a pair whose longer sequence has `length` residues, in a gang of g warps.
+extern "C" void osw_t16_block_geometry(uint32_t length, int g, int rmax, uint32_t *n_blocks, int *rows_per_lane) {
+    osw_t16::block_geometry((length + 31) / 32, g, rmax, n_blocks, rows_per_lane);
 }

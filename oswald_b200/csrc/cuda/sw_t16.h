@@ -37,7 +37,8 @@ struct OswT16Params {
 
 // Histogram of the shard's pairs by ceil(length of the longer sequence / 32): hist[OSW_T16_MAX_ROWS32 + 1].
 void osw_t16_histogram(const uint32_t *seq_len, uint64_t n_seqs, uint32_t *hist);
-// Plans the launch for the given queries; plan->warps == 0 when this form cannot take them.
-void osw_t16_plan(const uint32_t *hist, uint64_t n_seqs, const uint32_t *q_off, int nq, int n_sms, OswT16Plan *plan);
+// Plans the launch for the given queries; plan->warps == 0 when this form cannot take them.  gang_fraction: a pair
+// goes to the smallest gang that scores it within this fraction of the launch's estimated time (1.2 measured best on BASELINE.json config 1).
+void osw_t16_plan(const uint32_t *hist, uint64_t n_seqs, const uint32_t *q_off, int nq, int n_sms, double gang_fraction, OswT16Plan *plan);
 int  osw_launch_t16(const OswT16Params &p, const OswT16Plan &plan, int n_ctas, cudaStream_t st);
 #endif

@@ -16,7 +16,8 @@ from oswald_b200 import capi
 from oswald_b200.host import merge_hits
 
 AA = np.array([0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 21], dtype=np.uint8)
-MODES = [capi.OSW_K_DEFAULT, capi.OSW_K_DEFAULT | capi.OSW_K_TWO_TRACK, capi.OSW_K_DEFAULT | capi.OSW_K_PAIR_DB, capi.OSW_K_I32]
+MODES = [capi.OSW_K_DEFAULT, capi.OSW_K_DEFAULT | capi.OSW_K_TWO_TRACK, capi.OSW_K_DEFAULT | capi.OSW_K_PAIR_DB, capi.OSW_K_I32,
+         capi.OSW_K_DEFAULT | capi.OSW_K_TRANSPOSED]
 
 
 def main():
@@ -41,9 +42,14 @@ def main():
         alphabet = 24 if rng.random() < 0.2 else 20
         seqs = [(rng.integers(0, 24, size=int(l)).astype(np.uint8) if alphabet == 24 else AA[rng.integers(0, 20, size=int(l))]) for l in lens]
         nq = int(rng.integers(1, 10))
+        mode = MODES[int(rng.integers(0, len(MODES)))]
         qlens = []
         for _ in range(nq):
             r = rng.random()
+            if mode & capi.OSW_K_TRANSPOSED:          # the transposed form takes queries of up to 1024 residues, 4096 in all
+                qlens.append(0 if r < 0.05 else int(rng.integers(1, 40)) if r < 0.3 else int(rng.integers(40, 250)) if r < 0.85
+                             else int(rng.integers(250, 1025)))
+                continue
             qlens.append(0 if r < 0.05 else int(rng.integers(1, 40)) if r < 0.3 else int(rng.integers(40, 700)) if r < 0.8
                          else int(rng.integers(700, 3200)) if r < 0.97 else int(rng.integers(3200, 7000)))
         qs = [AA[rng.integers(0, 20, size=m)] for m in qlens]
@@ -58,7 +64,6 @@ def main():
         go, ge = (int(rng.integers(0, 40)), int(rng.integers(0, 8))) if rng.random() < 0.9 else (255, 127)
         top = int(rng.choice([0, 1, 5, 10, 64, len(seqs) + 3]))
         chunk = int(rng.choice([0, 0, 0, 16, 100, 700, 3000]))
-        mode = MODES[int(rng.integers(0, 4))]
         shards = 2 if rng.random() < 0.25 else 1
         want = O.search(q.residues, q.offsets, db.residues, db.offsets, O.matrix(name), go, ge)
         got = np.zeros_like(want)

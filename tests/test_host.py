@@ -213,6 +213,62 @@ def test_u16_dataflow_model_matches_oracle(G, R, chains):
         assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("gang,rmax", [(1, 4), (1, 8), (4, 4), (8, 8), (16, 4)])
+def test_t16_dataflow_model_matches_oracle(built, gang, rmax):
+    """The transposed scheme of sw_t16.cu (database residues as rows, skewed lanes, blocks handing their bottom row
+    on in place), modelled step by step in Python with the library's own block geometry."""
+    import emu_t16
+    rng = np.random.default_rng(16 * gang + rmax)
+    for trial in range(6):
+        name = ["blosum62", "pam30", "blosum45", "pam250"][trial % 4]
+        go, ge = [(10, 2), (9, 1), (14, 2), (0, 0), (255, 127)][trial % 5]
+        mat = O.matrix(name)
+        la = int(rng.integers(1, 40 * rmax * (3 if gang == 1 else 1) + 2))
+        lb = la + int(rng.integers(0, 70))                       # the pair's longer sequence sets the block count
+        a, b = AA[rng.integers(0, 20, size=la)], AA[rng.integers(0, 20, size=lb)]
+        q = AA[rng.integers(0, 20, size=int(rng.choice([1, 2, 31, 32, 33, 40, 75])))]
+        if trial % 2 == 0:
+            a = np.concatenate([a[: la // 2], q, a[la // 2:]])[:lb]
+        for seq in (a, b):
+            assert emu_t16.score_half(built, seq, lb, q, mat, go, ge, gang, rmax) == O.sw_score(q, seq, mat, go, ge)
+
+
+def test_t16_planner(built):
+    """Shapes (warps x rows per lane) by query length, gang classes along the descending length order."""
+    import ctypes as C
+    built.osw_t16_plan_probe.restype = C.c_int
+
+    def plan(lens, qlens, gang_fraction=1.2):
+        lens = np.sort(np.asarray(lens, dtype=np.uint32))
+        q_off = np.concatenate([[0], np.cumsum(qlens)]).astype(np.uint32)
+        cb, gs = (C.c_uint32 * 5)(), (C.c_int * 4)()
+        warps, rmax, est, padded = C.c_int(), C.c_int(), C.c_double(), C.c_uint64()
+        rc = built.osw_t16_plan_probe(lens.ctypes.data_as(C.c_void_p), C.c_uint64(len(lens)), q_off.ctypes.data_as(C.c_void_p), len(qlens), 148,
+                                      C.c_double(gang_fraction), cb, gs, C.byref(warps), C.byref(rmax), C.byref(est), C.byref(padded))
+        assert rc == 0
+        return list(cb), list(gs), warps.value, rmax.value, est.value, padded.value
+
+    rng = np.random.default_rng(5)
+    lens = np.exp(rng.normal(5.6, 0.6, size=10001)).astype(np.uint32).clip(1, 65535)
+    lens[:5] = 0
+    cb, gs, warps, rmax, est, padded = plan(lens, [144])
+    assert (warps, rmax) == (16, 4) and gs == [16, 8, 4, 1]
+    assert cb[0] == 0 and cb[4] == 5001 and all(cb[i] <= cb[i + 1] for i in range(4))          # every pair in exactly one class
+    assert cb[3] > 0 and cb[3] < 1000, "the longest pairs of a small database go to gangs, the bulk to lone warps"
+    assert 144 * int(lens.sum()) < padded < 2 * 144 * int(lens.sum()) and est > 0                 # padding rows and the array's skew
+    # a smaller fraction of the launch time per task: more pairs in gangs
+    assert plan(lens, [144], 0.5)[0][3] > cb[3] > plan(lens, [144], 3.0)[0][3]
+    # a large database: no task is long beside the launch
+    assert plan(np.tile(lens, 30), [144])[0][3] == 0
+    # shapes by query length: 16 x 4 while the rings fit beside the tables, then 8 x 8, then 8 x 4, then not at all
+    assert plan(lens, [250])[2:4] == (16, 4)
+    assert plan(lens, [400])[2:4] == (8, 8) and plan(lens, [400])[1] == [8, 4, 1, 1]
+    assert plan(lens, [1000])[2:4] == (8, 4)
+    assert plan(lens, [1025])[2] == 0 and plan(lens, [500] * 9)[2] == 0 and plan(lens, [0])[2] == 0
+    assert plan(lens, [97] * 9)[2:4] == (16, 4)
+    assert plan([], [144])[2] == 0
+
+
 def _cli():
     path = os.path.join(ROOT, "oswald_b200", "oswald")
     if not os.path.exists(path):
