@@ -118,12 +118,22 @@ topr_small_kernel(const int32_t *scores, const uint32_t *canon, uint32_t n, uint
     if (threadIdx.x == 0) { s_pre = 0; s_need = r; s_count = 0; s_or = 0; s_and = ~0ull; }
     __syncthreads();
     unsigned long long k_or = 0, k_and = ~0ull;
-    for (uint32_t i = threadIdx.x; i < n; i += SMALL_THREADS) {
-        const int sc = row[i];
-        if (sc == OSW_SCORE_FLAGGED && fl.count) list_flagged(fl, (uint32_t)q, i);
-        const unsigned long long k = make_key(sc, canon[i]);
-        s_keys[i] = k;
-        k_or |= k; k_and &= k;
+    for (uint32_t i0 = threadIdx.x; i0 < n; i0 += 4 * SMALL_THREADS) {          // (four independent loads in flight per thread)
+        int sc[4]; uint32_t cn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + u * SMALL_THREADS;
+            sc[u] = i < n ? row[i] : 0; cn[u] = i < n ? canon[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + u * SMALL_THREADS;
+            if (i >= n) break;
+            if (sc[u] == OSW_SCORE_FLAGGED && fl.count) list_flagged(fl, (uint32_t)q, i);
+            const unsigned long long k = make_key(sc[u], cn[u]);
+            s_keys[i] = k;
+            k_or |= k; k_and &= k;
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) { k_or |= __shfl_xor_sync(0xffffffffu, k_or, o); k_and &= __shfl_xor_sync(0xffffffffu, k_and, o); }

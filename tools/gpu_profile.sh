@@ -11,6 +11,14 @@ echo "launch list rc=$?"
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:sw_u16_kernel -s 14 -c 2 -f -o gpurun_out/${TAG} $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "full capture rc=$?"
+# the transposed form (sw_t16.cu) on BASELINE.json config 1: launch list of three searches, full capture of the kernel
+C1="python bench.py --config 1 --steps 3 --warmup 1 --no-cpu-baseline --no-extra --no-verify"
+$C1 > gpurun_out/${TAG}_plain5.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/${TAG}_launches_c1.csv $C1 > gpurun_out/${TAG}_ncu5.log 2>&1
+echo "config-1 launch list rc=$?"
+$C1 > gpurun_out/${TAG}_plain6.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:sw_t16 -s 2 -c 1 -f -o gpurun_out/${TAG}_t16 $C1 > gpurun_out/${TAG}_ncu6.log 2>&1
+echo "config-1 full capture rc=$?"
 FULL="python bench.py --steps 1 --warmup 0 --config ${CFG:-3} --no-cpu-baseline --no-extra --no-verify"
 $FULL > gpurun_out/${TAG}_plain4.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_full.csv $FULL > gpurun_out/${TAG}_ncu4.log 2>&1
