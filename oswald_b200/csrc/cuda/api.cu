@@ -30,7 +30,7 @@ constexpr uint32_t MAX_LAUNCH_SLOTS = 4096;
 constexpr uint32_t FLAG_CAPACITY_MIN = 1u << 16;
 constexpr size_t CONTROL_BYTES = MAX_LAUNCH_SLOTS * sizeof(unsigned long long) + 2 * sizeof(unsigned long long) + (1 + MAX_LAUNCH_SLOTS) * sizeof(uint32_t);
 
-struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; uint32_t express; uint32_t slot; uint32_t x_chunks, x_ctas; int x_R; uint32_t pipe_chunks; int transposed; };
+struct LaunchRecord { int G, R, has_in, has_out, pair_db; uint32_t first, end; uint64_t cols; uint32_t express; uint32_t slot; uint32_t x_chunks, x_ctas; int x_R; uint32_t pipe_chunks; int transposed; uint32_t x_slot; };
 
 struct DevState {
     int dev = -1, n_sms = 0;
@@ -151,7 +151,9 @@ struct Tunables {
     int      rmax = 0;                  // OSW_RMAX: rows per lane of the full-height passes (0 = default)
     int      long_chunks = -1;          // OSW_LONG_CHUNKS: force the number of chunks of the long-chunk launch (0 = never)
     int      pipe_chunks = -1;          // OSW_PIPE_CHUNKS: force the number of chunks whose passes are pipelined (0 = never)
-    int      transpose = -1;            // OSW_TRANSPOSE: 0 = never the transposed form (sw_t16.cu), 1 = whenever the queries fit it
+    int      transpose = -1;            // OSW_TRANSPOSE: 0 = never the transposed form (sw_t16.cu), 1 = whenever the queries fit it,
+                                        // 2 = only for the long chunks of the passes
+    double   t16_long_frac = 1.0;       // OSW_T16_LONG_FRAC: chunks whose contended walk exceeds this fraction of the launch's pipe time go to the transposed launch
     double   t16_gang = 1.2;            // OSW_T16_GANG: its gang threshold, as a fraction of the launch's estimated time
     bool     trace = false;             // OSW_TRACE: per-launch report on stderr
     void read() {
@@ -167,6 +169,7 @@ struct Tunables {
         if (const char *e = getenv("OSW_PIPE_CHUNKS")) pipe_chunks = atoi(e);
         if (const char *e = getenv("OSW_TRANSPOSE")) transpose = atoi(e);
         if (const char *e = getenv("OSW_T16_GANG")) t16_gang = atof(e);
+        if (const char *e = getenv("OSW_T16_LONG_FRAC")) t16_long_frac = atof(e);
         trace = getenv("OSW_TRACE") != nullptr;
     }
 };
@@ -556,9 +559,56 @@ struct LaunchModel {
     }
 };
 
+// Long chunks in the TRANSPOSED form (sw_t16.cu).  The chunks of a single-pass launch that could
+// not be walked among busy neighbours within the launch's pipe time hold the shard's longest sequences; a
+// transposed launch scores those pairs in a time that does not depend on their length (m + 31 steps per block
+// of 128 rows, gangs of warps for the longest), on as many SMs as balance it - with a margin: its model is the
+// less certain one, and an SM more costs the other launch under a per cent - against the launch that walks the
+// rest.  (The same kernel with the widest array needed one dependent step per column: on 100 000 sequences x one
+// short query its 15 SMs were still walking when the other 133 had been idle for a third of the search.)
+struct LongT16 { uint32_t n_chunks = 0, n_ctas = 0; OswT16Plan plan; double est = 0; };
+bool plan_long_t16(const osw_ctx *c, const DevState &d, const OswPass &ps, uint32_t first, uint32_t end, uint64_t cols,
+                   const uint32_t *q_off, int nq, LongT16 *out) {
+    const osw_shard &s = d.shard;
+    const bool pd = ps.pair_db != 0;
+    const osw_chunk *dir = pd ? s.pair_chunks : s.chunks;
+    auto chunk_cols = [&](uint32_t k) -> double { return pd ? (double)dir[k].n_pair_cols : (double)dir[k].n_cols; };
+    *out = LongT16();
+    if (end <= first || !c->tune.express || d.streaming || c->tune.long_chunks == 0) return false;
+    const LaunchModel m(ps.G, ps.R, pd, (double)cols, d.n_sms, (double)(end - first));
+    if (!(chunk_cols(first) * m.contended > c->tune.express_ratio * m.t_pipe)) return false;
+    const LaunchModel full(ps.G, ps.R, pd, (double)cols, d.n_sms);
+    double x_cols = 0;
+    uint32_t n = 0;
+    while (first + n < end && n < 16384u && chunk_cols(first + n) * full.contended > c->tune.t16_long_frac * full.t_pipe) { x_cols += chunk_cols(first + n); ++n; }
+    if (c->tune.long_chunks > 0) {          // experiments: force the number of chunks
+        n = std::min<uint32_t>((uint32_t)c->tune.long_chunks, end - first);
+        x_cols = 0;
+        for (uint32_t k = 0; k < n; ++k) x_cols += chunk_cols(first + k);
+    }
+    if (!n) return false;
+    // (chunks are in descending, sequences in ascending length order: the chunks' sequences are the last ones
+    // of the shard; a pair that straddles the cut is scored by both launches, with the same result)
+    const uint64_t N = s.n_seqs, s_cut = dir[first + n - 1].seq0 & ~1u;
+    std::vector<uint32_t> hist_x(OSW_T16_MAX_ROWS32 + 1);
+    osw_t16_histogram(s.seq_len + s_cut, N - s_cut, hist_x.data());
+    for (int k : {2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96}) {
+        if (k > d.n_sms - 16) break;
+        OswT16Plan pl;
+        osw_t16_plan(hist_x.data(), N - s_cut, q_off, nq, k, c->tune.t16_gang, &pl);
+        if (pl.warps != 16) break;
+        const double t_rest = full.t_pipe * ((double)cols - x_cols) / (double)std::max<uint64_t>(cols, 1) * d.n_sms / (d.n_sms - k);
+        const double t = std::max(t_rest, pl.est_cycles / 0.75);
+        if (!out->n_chunks || t < out->est) { out->est = t; out->plan = pl; out->n_ctas = (uint32_t)k; out->n_chunks = n; }
+    }
+    if (!out->n_chunks) return false;
+    out->plan.n_pairs = (uint32_t)((N + 1) / 2);
+    return true;
+}
+
 int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32_t *q_off, int nq,
                    const int8_t *matrix, int go, int ge, uint32_t top_r, bool want_all,
-                   const std::vector<OswPass> &passes, const OswPass *pass_x, const OswT16Plan *tplan,
+                   const std::vector<OswPass> &passes, const OswPass *pass_x, const OswT16Plan *tplan, bool t16_long,
                    uint32_t *n_launch_slots, uint64_t *launches, uint64_t *padded_cells) {
     const osw_shard &s = d.shard;
     const uint64_t N = s.n_seqs;
@@ -674,18 +724,20 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             // one warp per scheduler, so that they advance at the latency of a step rather than at a
             // quarter of the scheduler's issue rate.  (Threshold 1.5 measured: at a ratio of 1.15 the
             // express CTAs cost 4 %, at 1.9 they gain 6 %, at 3.5 and above 20-40 %.)
-            // When walking the longest chunk among three other busy warps would take clearly longer
-            // than the whole launch needs for its cell updates, the longest chunks get express CTAs:
-            // one warp per scheduler, so that they advance at the latency of a step rather than at a
-            // quarter of the scheduler's issue rate.  (Threshold 1.5 measured: at a ratio of 1.15 the
-            // express CTAs cost 4 %, at 1.9 they gain 6 %, at 3.5 and above 20-40 %.)
             up.express_ctas = 0; up.all_express = 0; up.progress_in = nullptr; up.progress_out = nullptr;
             uint32_t x_chunks = 0, x_ctas = 0;
+            bool x_t16 = false;               // the long-chunk launch in the transposed form
+            OswT16Plan xplan;
+            uint32_t x_slot = 0;
             if (end > first && c->tune.express && !reserved_ctas) {
                 const LaunchModel m(ps.G, ps.R, pd, (double)cols, d.n_sms, (double)(end - first));
                 const double longest = (double)chunk_cols(first);
                 if (longest * m.contended > c->tune.express_ratio * m.t_pipe) {
-                    if (pass_x && !d.streaming && passes.size() == 1 && (pass_x->G != ps.G || pass_x->R < ps.R) && c->tune.long_chunks != 0) {
+                    LongT16 lt;
+                    if (t16_long && passes.size() == 1 && plan_long_t16(c, d, ps, first, end, cols, q_off, nq, &lt)) {
+                        x_t16 = true; x_chunks = lt.n_chunks; x_ctas = lt.n_ctas; xplan = lt.plan;
+                    }
+                    if (!x_t16 && pass_x && !d.streaming && passes.size() == 1 && (pass_x->G != ps.G || pass_x->R < ps.R) && c->tune.long_chunks != 0) {
                         // Long-chunk launch: a step takes longer the more rows a lane holds (140 + 7 R cycles
                         // for a warp alone on its scheduler), so the chunks whose walk would outlast the
                         // launch go to a SECOND, concurrent launch of the same kernel with the widest array
@@ -730,18 +782,34 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
                 // fork: the long-chunk launch starts when everything enqueued so far (uploads, clears) is done
                 CK(cudaEventRecord(d.ev_ready[0], d.st));
                 CK(cudaStreamWaitEvent(d.st_copy, d.ev_ready[0], 0));
-                U16Params xp = up;
-                xp.profile = d.d_profile_x; xp.first_table = d.d_first_table_x; xp.all_express = 1;
-                xp.chunk_first = first; xp.chunk_end = first + x_chunks;
-                xp.chunk_counter = d.d_counters + 1 + slot; xp.cycle_acc = nullptr;
-                ++slot;
-                int rcx = osw_launch_u16(xp, *pass_x, (int)x_ctas, d.st_copy);
+                int rcx;
+                if (x_t16) {
+                    if (slot + OSW_T16_CLASSES >= MAX_LAUNCH_SLOTS) { snprintf(g_err, sizeof g_err, "too many launches"); return OSW_E_ARG; }
+                    OswT16Params tp;
+                    tp.stream = d.d_stream; tp.seq_off = d.d_seq_off; tp.seq_len = d.d_seq_len;
+                    tp.queries = d.d_queries; tp.q_off = d.d_qoff; tp.nq = nq; tp.matrix = d.d_matrix;
+                    tp.scores = d.d_scores; tp.n_seqs = N;
+                    tp.counters = d.d_counters + 1 + slot; tp.cycle_acc = d.d_cycles + slot;
+                    tp.gap_open_extend = go + ge; tp.gap_extend = ge;
+                    x_slot = slot;
+                    slot += OSW_T16_CLASSES;
+                    rcx = osw_launch_t16(tp, xplan, (int)x_ctas, d.st_copy);
+                    *launches += 1;
+                    *padded_cells += xplan.padded_cells;
+                } else {
+                    U16Params xp = up;
+                    xp.profile = d.d_profile_x; xp.first_table = d.d_first_table_x; xp.all_express = 1;
+                    xp.chunk_first = first; xp.chunk_end = first + x_chunks;
+                    xp.chunk_counter = d.d_counters + 1 + slot; xp.cycle_acc = nullptr;
+                    ++slot;
+                    rcx = osw_launch_u16(xp, *pass_x, (int)x_ctas, d.st_copy);
+                    *launches += 2;
+                }
                 if (rcx != OSW_OK) { cuda_fail(cudaGetLastError(), "long-chunk launch", __LINE__); return rcx; }
                 CK(cudaEventRecord(d.ev_free[0], d.st_copy));
-                *launches += 2;
                 uint64_t xc = 0;
                 for (uint32_t k = 0; k < x_chunks; ++k) xc += chunk_cols(first + k);
-                *padded_cells += (uint64_t)32 * pass_x->R * 2 * xc;
+                if (!x_t16) *padded_cells += (uint64_t)32 * pass_x->R * 2 * xc;
                 up.chunk_first = first + x_chunks;
                 cols -= xc;
             }
@@ -752,7 +820,7 @@ int enqueue_search(osw_ctx *c, DevState &d, const uint8_t *queries, const uint32
             int rc2 = osw_launch_u16(up, ps, d.n_sms - (int)x_ctas - (int)reserved_ctas, d.st);
             if (rc2 != OSW_OK) { cuda_fail(cudaGetLastError(), "sw_u16 launch", __LINE__); return rc2; }
             if (x_chunks) CK(cudaStreamWaitEvent(d.st, d.ev_free[0], 0));          // join
-            d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols, up.express_ctas, slot, x_chunks, x_ctas, x_chunks ? pass_x->R : 0, 0u});
+            d.trace.push_back({ps.G, ps.R, ps.has_in, ps.has_out, ps.pair_db, first, end, cols, up.express_ctas, slot, x_chunks, x_ctas, x_chunks ? (x_t16 ? -1 : pass_x->R) : 0, 0u, 0, x_slot});
             ++slot; *launches += 2;               // profile_build_kernel + sw_u16_kernel
             *padded_cells += (uint64_t)ps.G * ps.R * 2 * cols;
             return OSW_OK;
@@ -1028,6 +1096,7 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
     // databases, whose launches last as long as the walk along their longest sequence, above all.
     std::vector<OswT16Plan> tplans;
     double t16_est = 0;
+    bool t16_long = false;                // the passes' long-chunk launch may take the transposed form
     if (use_u16 && c->tune.transpose != 0 && !(c->kernel_mask & (OSW_K_TWO_TRACK | OSW_K_PAIR_DB))) {
         bool ok = true;
         for (int i = 0; i < c->n_dev; ++i) ok &= !c->devs[i].streaming && (c->devs[i].shard.n_seqs == 0 || c->devs[i].d_stream != nullptr);
@@ -1044,6 +1113,8 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
             }
         }
         const bool forced = (c->kernel_mask & OSW_K_TRANSPOSED) || c->tune.transpose == 1;
+        t16_long = ok && !forced && tplans[0].warps == 16 && passes.size() == 1;
+        if (ok && !forced && c->tune.transpose == 2) ok = false;          // (experiments: the transposed form for long chunks only)
         if (ok && !forced) {
             // the passes' own estimate, on the first GPU's shard (all shards hold the same mix of lengths)
             const DevState &d0 = c->devs[0];
@@ -1061,6 +1132,11 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
             // 0.95-1.1 for the transposed form's; 8-warp CTAs - queries of more than about 250 residues - have two
             // warps per scheduler and are slower than the passes everywhere: profiles/r2_transposed_form.md)
             ok = s0.n_seqs != 0 && tplans[0].warps == 16 && tplans[0].est_cycles < 1.4 * t_std;
+            // ... and against the passes with their long chunks in the transposed form, when that applies (measured
+            // / model there: 1.4 on 50 000-100 000 sequences, 1.8 on 10 000)
+            LongT16 lt;
+            if (ok && t16_long && plan_long_t16(c, d0, passes[0], 0, pd ? s0.n_pair_chunks : s0.n_chunks, pd ? s0.pair_cols : s0.n_residues, q_off, nq, &lt))
+                ok = tplans[0].est_cycles < 1.3 * lt.est;
         }
         if (!ok) tplans.clear();
         else t16_est = tplans[0].est_cycles;
@@ -1071,7 +1147,7 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
     // ---- phase 1: first stage on every GPU ------------------------------------------------
     for (int i = 0; i < c->n_dev; ++i) {
         int rc = enqueue_search(c, c->devs[i], queries, q_off, nq, matrix, go, ge, (uint32_t)top_r,
-                                all_scores != nullptr, passes, have_x ? &plan_x : nullptr, tplans.empty() ? nullptr : &tplans[(size_t)i],
+                                all_scores != nullptr, passes, have_x ? &plan_x : nullptr, tplans.empty() ? nullptr : &tplans[(size_t)i], t16_long && tplans.empty(),
                                 &slots[i], &launches, &padded);
         if (rc != OSW_OK) return rc;
     }
@@ -1189,9 +1265,11 @@ static int search_batch(osw_ctx *c, const uint8_t *queries, const uint32_t *q_of
                     continue;
                 }
                 const double cells = 2.0 * lr.G * lr.R * (double)lr.cols;
-                fprintf(stderr, "osw trace: launch %u/%zu G=%d R=%d in=%d out=%d pairdb=%d express=%u long[R=%d chunks=%u ctas=%u] pipelined=%u chunks [%u,%u)  %llu busy cycles/SM  %.2f padded cells/SM-clk\n",
+                fprintf(stderr, "osw trace: launch %u/%zu G=%d R=%d in=%d out=%d pairdb=%d express=%u long[R=%d (-1: transposed) chunks=%u ctas=%u] pipelined=%u chunks [%u,%u)  %llu busy cycles/SM  %.2f padded cells/SM-clk",
                         k + 1, d.trace.size(), lr.G, lr.R, lr.has_in, lr.has_out, lr.pair_db, lr.express, lr.x_R, lr.x_chunks, lr.x_ctas, lr.pipe_chunks, lr.first, lr.end,
                         cyc / d.n_sms, cells / (double)cyc);
+                if (lr.x_R < 0 && lr.x_ctas) fprintf(stderr, "  (%llu cycles per CTA here, %llu in the transposed launch)", cyc / (d.n_sms - lr.x_ctas), d.h_cycles[lr.x_slot] / lr.x_ctas);
+                fprintf(stderr, "\n");
             }
         }
         const uint32_t r = (uint32_t)std::min<uint64_t>((uint64_t)top_r, N);

@@ -547,13 +547,16 @@ def test_forced_group_widths(built, monkeypatch, min_g):
                 check(s, db, q, "blosum62", 10, 2, 10, mask=mode)
 
 
+@pytest.mark.parametrize("transpose", ["0", "2"])
 @pytest.mark.parametrize("n_long", ["3", "100000"])
-def test_long_chunk_launch(built, monkeypatch, n_long):
+def test_long_chunk_launch(built, monkeypatch, n_long, transpose):
     """Small databases: the longest chunks of a chain-bound single-pass launch go to a second, concurrent
-    launch with the widest array (32 lanes x 8..16 rows, every CTA an express CTA) - forced here to take a
-    few chunks / every chunk: one or several queries, both uses of the packed halves, empty and long
-    sequences, overflow, tiny chunks."""
+    launch - of the same kernel with the widest array (32 lanes x 8..16 rows, every CTA an express CTA), or
+    (transpose = 2, mode "auto", queries that fit it) in the transposed form, which scores the pairs of
+    sequences those chunks hold - forced here to take a few chunks / every chunk: one or several queries, both
+    uses of the packed halves, empty and long sequences, overflow, tiny chunks."""
     monkeypatch.setenv("OSW_LONG_CHUNKS", n_long)
+    monkeypatch.setenv("OSW_TRANSPOSE", transpose)
     monkeypatch.setenv("OSW_EXPRESS_RATIO", "0")            # every launch counts as chain-bound
     rng = np.random.default_rng(77 + int(n_long))
     W = np.uint8(19)
