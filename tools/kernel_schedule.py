@@ -27,10 +27,14 @@ KERNELS = {
     "two_track_G32_R20": "_ZN7osw_u1613sw_u16_kernelILi32ELi20ELi512ELb0ELb0ELb0EEEvNS_5KArgsE",
     "pair_db_G32_R28": "_ZN7osw_u1613sw_u16_kernelILi32ELi28ELi512ELb1ELb0ELb0EEEvNS_5KArgsE",
     "pair_db_G4_R36": "_ZN7osw_u1613sw_u16_kernelILi4ELi36ELi384ELb1ELb0ELb0EEEvNS_5KArgsE",
+    # the transposed form's 16-warp instance: the sweep of 4 rows per lane that hands its bottom row on in
+    # place, both ends of the array inside the query (two steps per trip: 24 add-max, one ring read and one
+    # ring write per step) - what small databases spend their time in
+    "transposed_R4_in_place": ("_ZN7osw_t1613sw_t16_kernelILi4EEEvNS_5TArgsE", {"VIADDMNMX.U16x2": 24, "STS.64": 2, "LDS.64": 2}),
 }
 
 
-def step_loop(lib, fun):
+def step_loop(lib, fun, select=None):
     out = subprocess.run(["cuobjdump", "-sass", "-fun", fun, lib], capture_output=True, text=True, check=True).stdout
     ops = []
     for line in out.splitlines():
@@ -47,6 +51,10 @@ def step_loop(lib, fun):
     def dpx(lo, hi):
         return sum(1 for a, t in ops if lo <= a <= hi and "VIADDMNMX" in t)
     big = sorted((hi - lo, lo, hi) for lo, hi in loops if dpx(lo, hi) >= 12)
+    if select:        # ... or the smallest loop with exactly these opcode counts
+        def mix(lo, hi):
+            return collections.Counter((t.split()[1] if t.startswith("@") else t.split()[0]) for a, t in ops if lo <= a <= hi)
+        big = [(n, lo, hi) for n, lo, hi in big if all(mix(lo, hi).get(k, 0) == v for k, v in select.items())]
     if not big:
         raise RuntimeError("no step loop found in " + fun)
     _, lo, hi = big[0]
@@ -71,7 +79,10 @@ def fingerprints(lib):
     res = resources(lib)
     out = {}
     for name, fun in KERNELS.items():
-        seq = step_loop(lib, fun)
+        select = None
+        if isinstance(fun, tuple):
+            fun, select = fun
+        seq = step_loop(lib, fun, select)
         mix = collections.Counter(seq)
         out[name] = {"registers": res[fun][0], "stack": res[fun][1], "loop_instructions": len(seq),
                      "viaddmnmx_u16x2": mix.get("VIADDMNMX.U16x2", 0), "vimnmx3_u16x2": mix.get("VIMNMX3.U16x2", 0),
